@@ -1,12 +1,14 @@
 """Loader for the product's C-ABI library. There is no CPU fallback: a missing library is an error."""
 from __future__ import annotations
 
-import ctypes
+import ctypes as C
 import os
 from typing import Optional
 
+from .api import Api
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB: Optional[ctypes.CDLL] = None
+_LIB: Optional[C.CDLL] = None
 _API = None
 
 
@@ -14,7 +16,7 @@ def library_path() -> str:
     return os.path.join(_HERE, "csrc", "libcg_b200.so")
 
 
-def load_library() -> ctypes.CDLL:
+def load_library() -> C.CDLL:
     """dlopen csrc/libcg_b200.so (built by `make -C computational-graph_b200/csrc` or
     `__graft_entry__.build()`). Raises — never falls back — when it is absent."""
     global _LIB
@@ -24,14 +26,85 @@ def load_library() -> ctypes.CDLL:
             raise RuntimeError(
                 f"{path} is missing: build the sm_100a CUDA library first "
                 "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
-        _LIB = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+        _LIB = C.CDLL(path)
     return _LIB
 
 
-def get_api():
+class PlanStats(C.Structure):
+    """`cg_plan_stats` (include/cg_graph.h)."""
+    _fields_ = [(n, C.c_ulonglong) for n in ("tape_instrs", "live_instrs", "kernels_per_iter", "ew_kernels", "gemms",
+                                             "gemms_fused_sgd", "reduces", "arena_bytes")] + \
+               [("gemm_flop_per_iter", C.c_double), ("ew_bytes_per_iter", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class ProductApi(Api):
+    """`Api` over the `cg_*` symbols plus the product-only switches and introspection."""
+
+    def __init__(self, lib: C.CDLL):
+        super().__init__(lib, "cg_")
+        for name in ("set_tf32", "set_fix_act_grad", "set_fuse", "set_cuda_graph", "set_strict_gemm_max"):
+            fn = self._sym(name)
+            fn.restype, fn.argtypes = None, [C.c_int]
+        lib.cg_launch_count.restype = C.c_ulonglong
+        lib.cg_plan_stats_get.restype, lib.cg_plan_stats_get.argtypes = C.c_int, [C.c_void_p, C.c_float, C.POINTER(PlanStats)]
+        lib.cg_time_iterations.restype = C.c_double
+        lib.cg_time_iterations.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
+        lib.cg_minimize_async.restype, lib.cg_minimize_async.argtypes = C.c_int, [C.c_void_p, C.c_float, C.c_int]
+        lib.cg_synchronize.restype = C.c_int
+        lib.cg_leaf_set.restype, lib.cg_leaf_set.argtypes = C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+        lib.cg_set_device.restype, lib.cg_set_device.argtypes = C.c_int, [C.c_int]
+        lib.cg_dp_unique_id.restype, lib.cg_dp_unique_id.argtypes = C.c_int, [C.c_char_p]
+        lib.cg_dp_init.restype, lib.cg_dp_init.argtypes = C.c_int, [C.c_int, C.c_int, C.c_char_p]
+        lib.cg_dp_shutdown.restype = C.c_int
+
+    def _check(self, rc: int):
+        if rc != 0:
+            from .api import GraphError
+            raise GraphError(self._last_error().decode())
+
+    def set_tf32(self, on: bool): self.lib.cg_set_tf32(int(on))
+    def set_fix_act_grad(self, on: bool): self.lib.cg_set_fix_act_grad(int(on))
+    def set_fuse(self, on: bool): self.lib.cg_set_fuse(int(on))
+    def set_cuda_graph(self, on: bool): self.lib.cg_set_cuda_graph(int(on))
+    def set_strict_gemm_max(self, dim: int): self.lib.cg_set_strict_gemm_max(int(dim))
+    def set_device(self, dev: int): self._check(self.lib.cg_set_device(int(dev)))
+    def launch_count(self) -> int: return int(self.lib.cg_launch_count())
+    def synchronize(self): self._check(self.lib.cg_synchronize())
+
+    def plan_stats(self, f, learn_rate: float) -> dict:
+        st = PlanStats()
+        self._check(self.lib.cg_plan_stats_get(f._h, float(learn_rate), C.byref(st)))
+        return st.as_dict()
+
+    def time_iterations(self, f, learn_rate: float, warmup: int, reps: int) -> float:
+        """ms per iteration, CUDA events on the library stream (inputs already resident in HBM)."""
+        ms = self.lib.cg_time_iterations(f._h, float(learn_rate), int(warmup), int(reps))
+        if ms < 0:
+            self._check(-1)
+        return ms
+
+    def minimize_async(self, f, learn_rate: float, iters: int):
+        self._check(self.lib.cg_minimize_async(f._h, float(learn_rate), int(iters)))
+
+    # data parallel ------------------------------------------------------------------------------
+    def dp_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.cg_dp_unique_id(buf))
+        return buf.raw
+
+    def dp_init(self, rank: int, world: int, uid: bytes):
+        self._check(self.lib.cg_dp_init(int(rank), int(world), uid))
+
+    def dp_shutdown(self):
+        self._check(self.lib.cg_dp_shutdown())
+
+
+def get_api() -> ProductApi:
     """The `Api` bound to the product library's `cg_*` symbols."""
     global _API
     if _API is None:
-        from .api import Api
-        _API = Api(load_library(), "cg_")
+        _API = ProductApi(load_library())
     return _API

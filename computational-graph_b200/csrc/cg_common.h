@@ -1,0 +1,129 @@
+// cg_common.h — shared declarations for libcg_b200.so (host + device).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+namespace cg {
+
+// Host-side failure = the reference's `panic!` / `check()`; the C ABI turns it into an error code.
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+  if (e != cudaSuccess) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %s (%s) at %s:%d", cudaGetErrorString(e), what, file, line);
+    throw Error(buf);
+  }
+}
+#define CG_CUDA(x) ::cg::cuda_check((x), #x, __FILE__, __LINE__)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ------------------------------------------------------------------------------------------------
+// Fused-elementwise bytecode (executed by ew_program_kernel, kernels_ew.cu).
+//
+// An accumulator machine over per-thread vectors of EW_VEC floats: one accumulator `acc` and EW_REGS
+// vector registers r[0..EW_REGS). Inputs are prefetched into r[0..n_in) before the first instruction
+// (all loads in flight at once); every instruction is (opcode << 4) | operand, operand < 16.
+// Every arithmetic opcode is a single IEEE f32 operation (no FMA contraction), so a fused chain is
+// bit-identical to the reference's one-kernel-per-node evaluation (src/cpu/ops.cpp:68-86).
+// ------------------------------------------------------------------------------------------------
+constexpr int EW_REGS = 12;
+constexpr int EW_MAX_IN = 12;
+constexpr int EW_MAX_OUT = 12;
+constexpr int EW_MAX_INS = 160;
+constexpr int EW_MAX_IMM = 8;
+
+enum EwOpcode : uint8_t {
+  OP_END = 0,
+  OP_LDR,      // acc = r[k]
+  OP_STR,      // r[k] = acc
+  OP_LDI,      // acc = imm[k]
+  OP_ADD,      // acc = acc + r[k]
+  OP_SUB,      // acc = acc - r[k]
+  OP_RSUB,     // acc = r[k] - acc
+  OP_MUL,      // acc = acc * r[k]
+  OP_MULI,     // acc = acc * imm[k]
+  OP_NEG,      // acc = -acc
+  OP_SQ,       // acc = acc * acc
+  OP_ABS_M,    // matrix path: x < 0 ? -x : x            (cpu/ops.cpp:70; abs(-0) = -0)
+  OP_SGN_M,    // matrix path: x < 0 ? -1 : 1            (cpu/ops.cpp:71; signum(+-0) = +1)
+  OP_ABS_S,    // scalar path: f32::abs                  (ops.rs:331; abs(-0) = +0)
+  OP_SGN_S,    // scalar path: f32::signum               (ops.rs:332; signum(-0) = -1, NaN -> NaN)
+  OP_SIGMOID,  // 1.0f / (1.0f + expf(-x))               (cpu/ops.cpp:72)
+  OP_TANH,     // tanhf(x)                               (cpu/ops.cpp:73)
+  OP_ONE_MINUS,// 1.0f - x                               (cpu/ops.cpp:74)
+  OP_STG,      // out[k][i] = acc
+  OP_COUNT
+};
+
+struct EwProgram {
+  uint64_t n;                       // elements in the iteration domain
+  uint32_t n_in, n_out, n_ins;
+  uint32_t in_scalar_mask;          // bit k: input k is a 1-element buffer broadcast to every element
+  const float* in[EW_MAX_IN];
+  float* out[EW_MAX_OUT];
+  float imm[EW_MAX_IMM];
+  uint16_t code[EW_MAX_INS];        // (opcode << 4) | operand
+};
+
+inline uint16_t ew_encode(EwOpcode op, int k = 0) { return (uint16_t)((op << 4) | (k & 0xf)); }
+
+// ------------------------------------------------------------------------------------------------
+// Kernel launchers (all asynchronous on `stream`). Column-major f32 everywhere.
+// ------------------------------------------------------------------------------------------------
+void launch_ew_program(const EwProgram& p, cudaStream_t stream);
+
+// dst (1 element) = reduce_sum(src[0..n)) / n   — the reference's `avg` (ops.rs:438-442, cpu/ops.cpp:138-145).
+// n <= kStrictReduceMax: one thread, sequential f32 sum (bit-identical to the reference's loop);
+// larger: float4 loads -> warp shuffle -> block -> ordered final pass (deterministic, pairwise rounding).
+constexpr size_t kStrictReduceMax = 4096;
+void launch_reduce_avg(const float* src, size_t n, float* dst, float* workspace, cudaStream_t stream);
+// dst = reduce_sum(src) / denom (denom = 1 gives the plain reduce_sum of cpu/ops.cpp:138-145)
+void launch_reduce_div(const float* src, size_t n, float denom, float* dst, float* workspace, cudaStream_t stream);
+size_t reduce_workspace_floats();
+
+// flag[0] = all(src == x) / all(src < x)  (cpu/ops.cpp:118-136); flag is a device int
+void launch_all_equal(const float* src, size_t n, float x, int* flag, cudaStream_t stream);
+void launch_all_less_than(const float* src, size_t n, float x, int* flag, cudaStream_t stream);
+
+// dst(column-major h x w) <- src(row-major h x w)   (set_array(transpose=true), cpu/matrix.cpp:26-36)
+void launch_rowmajor_to_colmajor(const float* src_rowmajor, float* dst_colmajor, unsigned h, unsigned w,
+                                 cudaStream_t stream);
+
+// C(m x n) = op(A) . op(B), column-major; lda/ldb/ldc = stored heights.
+//   strict = true : every output element is accumulated k-ascending with separate f32 multiply and add
+//                   roundings — bit-identical to the reference's naive gemm (cpu/ops.cpp:103-114).
+//   strict = false: tiled FP32 SIMT with FMA accumulation.
+struct GemmEpilogue {
+  // mode 0: C = acc.
+  // mode 1 (fused SGD, optimize.rs:149-152): C = C - (acc * lr), two roundings (never an FMA).
+  // mode 2 (dag-mode error accumulation): C = C + acc.
+  int mode = 0;
+  float lr = 0.0f;
+};
+void launch_gemm_f32(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda, int ldb,
+                     int ldc, bool strict, const GemmEpilogue& epi, cudaStream_t stream);
+
+// TF32 tensor-core path (tcgen05 + TMA + TMEM, gemm_tcgen05.cu). Returns false when the shape is not
+// eligible (caller falls back to launch_gemm_f32).
+bool gemm_tf32_eligible(int m, int n, int k, bool ta, bool tb);
+void launch_gemm_tf32(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda,
+                      int ldb, int ldc, const GemmEpilogue& epi, cudaStream_t stream);
+
+// Shape-based dispatch: strict (max(m,n,k) <= Runtime::strict_gemm_max) | tcgen05 TF32 (allow_tf32 and
+// eligible) | tiled FP32 SIMT.
+void launch_gemm(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda, int ldb,
+                 int ldc, const GemmEpilogue& epi, bool allow_tf32, cudaStream_t stream);
+
+// Data-parallel sum-allreduce of a weight gradient over NCCL (dp.cpp). In place.
+void dp_allreduce_sum(float* buf, size_t n, cudaStream_t stream);
+bool dp_enabled();
+
+}  // namespace cg

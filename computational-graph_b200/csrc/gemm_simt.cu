@@ -1,0 +1,214 @@
+// gemm_simt.cu — FP32 SIMT matrix product C = op(A) . op(B), column-major, NN / NT / TN / TT.
+//
+// Replaces the reference's cublasSgemm call (src/gpu/ops.cu:82-141) and restates the CPU gemm
+// (src/cpu/ops.cpp:88-116) for shapes the reference itself cannot run (non-square operands, Q7).
+// Forward products are NN, the two backward products of optimize.rs:196-200 are NT (E . W^T) and
+// TN (X^T . E). Two kernels:
+//   * gemm_strict_kernel — one thread per output element, k ascending, separate multiply and add
+//     roundings: bit-identical to the reference's naive triple loop. Used for small products where
+//     the latency of the launch dominates anyway (README LSTM, d <= 64).
+//   * gemm_tiled_kernel  — 128x128x16 shared-memory tiles, 8x8 register micro-tiles, double-buffered,
+//     FMA accumulation (k ascending per output element). FMA-pipe bound.
+// The tensor-core TF32 path lives in gemm_tcgen05.cu.
+#include "cg_common.h"
+
+namespace cg {
+
+__device__ __forceinline__ float epilogue_apply(const GemmEpilogue& epi, float acc, float old) {
+  if (epi.mode == 1) {
+    // optimize.rs:149-152: error *= lr; value -= error — two roundings, never an FMA
+    return __fsub_rn(old, __fmul_rn(acc, epi.lr));
+  }
+  if (epi.mode == 2) return __fadd_rn(old, acc);
+  return acc;
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_strict_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                          float* __restrict__ C, int m, int n, int k, int lda, int ldb,
+                                                          int ldc, GemmEpilogue epi) {
+  const int i = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int j = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (i >= m || j >= n) return;
+  float acc = 0.0f;
+  for (int kk = 0; kk < k; kk++) {
+    const float a = TA ? A[(size_t)i * lda + kk] : A[(size_t)kk * lda + i];
+    const float b = TB ? B[(size_t)kk * ldb + j] : B[(size_t)j * ldb + kk];
+    acc = __fadd_rn(acc, __fmul_rn(a, b));
+  }
+  float* c = C + (size_t)j * ldc + i;
+  *c = epilogue_apply(epi, acc, epi.mode != 0 ? *c : 0.0f);
+}
+
+constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+
+// Loads a (BK x TILE) operand tile into registers: element (kk, x) of the tile is op(M)(x0 + x, k0 + kk)
+// for A (x = row of C) or op(M)(k0 + kk, x0 + x) for B (x = column of C).
+//   MN_CONTIG: the stored matrix is contiguous along x (A not transposed, or B transposed).
+//   otherwise : contiguous along k.
+template <bool MN_CONTIG>
+__device__ __forceinline__ void load_tile(const float* __restrict__ M, int ld, int x0, int k0, int xmax, int kmax,
+                                          bool fast, float (&reg)[8]) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const int f = t + s * 256;
+    if (MN_CONTIG) {
+      const int kk = f >> 5, x4 = (f & 31) * 4;
+      const float* p = M + (size_t)(k0 + kk) * ld + x0 + x4;
+      if (fast) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        reg[s * 4 + 0] = v.x; reg[s * 4 + 1] = v.y; reg[s * 4 + 2] = v.z; reg[s * 4 + 3] = v.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++) reg[s * 4 + c] = (k0 + kk < kmax && x0 + x4 + c < xmax) ? p[c] : 0.0f;
+      }
+    } else {
+      const int x = f >> 2, k4 = (f & 3) * 4;
+      const float* p = M + (size_t)(x0 + x) * ld + k0 + k4;
+      if (fast) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        reg[s * 4 + 0] = v.x; reg[s * 4 + 1] = v.y; reg[s * 4 + 2] = v.z; reg[s * 4 + 3] = v.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++) reg[s * 4 + c] = (x0 + x < xmax && k0 + k4 + c < kmax) ? p[c] : 0.0f;
+      }
+    }
+  }
+}
+
+template <bool MN_CONTIG>
+__device__ __forceinline__ void store_tile(float (*S)[BM + PAD], const float (&reg)[8]) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const int f = t + s * 256;
+    if (MN_CONTIG) {
+      const int kk = f >> 5, x4 = (f & 31) * 4;
+      *reinterpret_cast<float4*>(&S[kk][x4]) = make_float4(reg[s * 4], reg[s * 4 + 1], reg[s * 4 + 2], reg[s * 4 + 3]);
+    } else {
+      const int x = f >> 2, k4 = (f & 3) * 4;
+#pragma unroll
+      for (int c = 0; c < 4; c++) S[k4 + c][x] = reg[s * 4 + c];
+    }
+  }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_tiled_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                         float* __restrict__ C, int m, int n, int k, int lda, int ldb,
+                                                         int ldc, GemmEpilogue epi) {
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+  static_assert(BM == BN, "store_tile assumes equal tile widths");
+
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int ri = threadIdx.x & 15, cj = threadIdx.x >> 4;
+
+  // fast path: whole tile in range, 16-byte aligned float4 loads
+  const bool a_al = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 4 == 0);
+  const bool b_al = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 4 == 0);
+  const bool m_full = m0 + BM <= m, n_full = n0 + BN <= n;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+
+  float ra[8], rb[8];
+  const int ktiles = (k + BK - 1) / BK;
+  {
+    const bool kf = BK <= k;
+    load_tile<!TA>(A, lda, m0, 0, m, k, a_al && m_full && kf, ra);
+    load_tile<TB>(B, ldb, n0, 0, n, k, b_al && n_full && kf, rb);
+    store_tile<!TA>(As[0], ra);
+    store_tile<TB>(Bs[0], rb);
+  }
+  __syncthreads();
+
+  for (int kt = 0; kt < ktiles; kt++) {
+    const int cur = kt & 1;
+    if (kt + 1 < ktiles) {
+      const int k0 = (kt + 1) * BK;
+      const bool kf = k0 + BK <= k;
+      load_tile<!TA>(A, lda, m0, k0, m, k, a_al && m_full && kf, ra);
+      load_tile<TB>(B, ldb, n0, k0, n, k, b_al && n_full && kf, rb);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      float a[8], b[8];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][kk][ri * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][kk][64 + ri * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][kk][cj * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][kk][64 + cj * 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < ktiles) {
+      store_tile<!TA>(As[cur ^ 1], ra);
+      store_tile<TB>(Bs[cur ^ 1], rb);
+    }
+    __syncthreads();
+  }
+
+  const bool c_al = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (ldc % 4 == 0);
+#pragma unroll
+  for (int jh = 0; jh < 2; jh++)
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const int j = n0 + jh * 64 + cj * 4 + jj;
+      if (j >= n) continue;
+#pragma unroll
+      for (int ih = 0; ih < 2; ih++) {
+        const int i = m0 + ih * 64 + ri * 4;
+        float* c = C + (size_t)j * ldc + i;
+        const float* v = &acc[ih * 4][jh * 4 + jj];  // acc[ih*4 + ii][jh*4 + jj], stride 8
+        if (c_al && i + 4 <= m) {
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (epi.mode != 0) o = *reinterpret_cast<const float4*>(c);
+          float4 w;
+          w.x = epilogue_apply(epi, v[0], o.x);
+          w.y = epilogue_apply(epi, v[8], o.y);
+          w.z = epilogue_apply(epi, v[16], o.z);
+          w.w = epilogue_apply(epi, v[24], o.w);
+          *reinterpret_cast<float4*>(c) = w;
+        } else {
+#pragma unroll
+          for (int ii = 0; ii < 4; ii++)
+            if (i + ii < m) c[ii] = epilogue_apply(epi, v[ii * 8], epi.mode != 0 ? c[ii] : 0.0f);
+        }
+      }
+    }
+}
+
+template <bool TA, bool TB>
+static void launch_t(const float* A, const float* B, float* C, int m, int n, int k, int lda, int ldb, int ldc, bool strict,
+                     const GemmEpilogue& epi, cudaStream_t stream) {
+  if (strict) {
+    dim3 grid((m + 15) / 16, (n + 15) / 16);
+    gemm_strict_kernel<TA, TB><<<grid, 256, 0, stream>>>(A, B, C, m, n, k, lda, ldb, ldc, epi);
+  } else {
+    dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN);
+    gemm_tiled_kernel<TA, TB><<<grid, 256, 0, stream>>>(A, B, C, m, n, k, lda, ldb, ldc, epi);
+  }
+  CG_CUDA(cudaGetLastError());
+}
+
+void launch_gemm_f32(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda, int ldb,
+                     int ldc, bool strict, const GemmEpilogue& epi, cudaStream_t stream) {
+  if (m == 0 || n == 0) return;
+  if (ta) {
+    if (tb) launch_t<true, true>(A, B, C, m, n, k, lda, ldb, ldc, strict, epi, stream);
+    else launch_t<true, false>(A, B, C, m, n, k, lda, ldb, ldc, strict, epi, stream);
+  } else {
+    if (tb) launch_t<false, true>(A, B, C, m, n, k, lda, ldb, ldc, strict, epi, stream);
+    else launch_t<false, false>(A, B, C, m, n, k, lda, ldb, ldc, strict, epi, stream);
+  }
+}
+
+}  // namespace cg

@@ -1,0 +1,293 @@
+// graph.cpp — graph construction with the reference's semantics (function.rs, ops.rs constructors).
+#include "graph.h"
+
+#include <cmath>
+#include <cstring>
+#include <unordered_set>
+
+namespace cg {
+
+DevBuf::~DevBuf() {
+  if (owned && ptr) cudaFree(ptr);
+}
+BufRef DevBuf::alloc(size_t n) {
+  auto b = std::make_shared<DevBuf>();
+  b->n = n;
+  b->owned = true;
+  CG_CUDA(cudaMalloc(&b->ptr, (n ? n : 1) * sizeof(float)));
+  return b;
+}
+
+Runtime& Runtime::get() {
+  static Runtime rt;
+  if (!rt.stream) rt.init();
+  return rt;
+}
+void Runtime::init() {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw Error("libcg_b200: no CUDA device available — this backend has no CPU fallback");
+  CG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CG_CUDA(cudaMalloc(&flag, 16 * sizeof(int)));  // [0] comparison flag, [4] reduce_sum result
+  CG_CUDA(cudaMalloc(&red_ws, reduce_workspace_floats() * sizeof(float)));
+  CG_CUDA(cudaMemset(red_ws, 0, reduce_workspace_floats() * sizeof(float)));
+  if (const char* s = getenv("CG_MODE")) mode = (strcmp(s, "dag") == 0) ? 1 : 0;
+  if (const char* s = getenv("CG_TF32")) tf32 = atoi(s);
+  if (const char* s = getenv("CG_FIX_ACT_GRAD")) fix_act_grad = atoi(s);
+  if (const char* s = getenv("CG_FUSE")) fuse = atoi(s);
+  if (const char* s = getenv("CG_CUDA_GRAPH")) use_graph = atoi(s);
+}
+
+static void fill_device(float* ptr, size_t n, float v) {
+  Runtime& rt = Runtime::get();
+  EwProgram p{};
+  p.n = n;
+  p.n_in = 0;
+  p.n_out = 1;
+  p.out[0] = ptr;
+  p.imm[0] = v;
+  p.code[0] = ew_encode(OP_LDI, 0);
+  p.code[1] = ew_encode(OP_STG, 0);
+  p.n_ins = 2;
+  launch_ew_program(p, rt.stream);
+}
+
+// ---- leaves -------------------------------------------------------------------------------------------
+static Function* new_leaf(Kind kind, const char* name, Value v) {
+  auto* f = new Function();
+  f->value = std::move(v);
+  f->has_params = (kind == Kind::Param || kind == Kind::Input);
+  f->body = std::make_shared<Expr>();
+  f->body->kind = kind;
+  if (name) f->body->name = name;
+  return f;
+}
+
+Function* make_scalar_leaf(Kind kind, const char* name, float x) {
+  Runtime& rt = Runtime::get();
+  Value v;
+  v.is_matrix = false;
+  v.uniform = true;
+  v.uval = x;
+  v.buf = DevBuf::alloc(1);
+  CG_CUDA(cudaMemcpyAsync(v.buf->ptr, &x, sizeof(float), cudaMemcpyHostToDevice, rt.stream));
+  CG_CUDA(cudaStreamSynchronize(rt.stream));
+  return new_leaf(kind, name, std::move(v));
+}
+
+void value_upload_rowmajor(Value& v, const float* src) {
+  // Matrix::new -> set_array(values, transpose = true) (matrix.rs:59-66, cpu/matrix.cpp:26-36)
+  Runtime& rt = Runtime::get();
+  const size_t n = v.size();
+  if (!v.is_matrix) {
+    CG_CUDA(cudaMemcpyAsync(v.buf->ptr, src, sizeof(float), cudaMemcpyHostToDevice, rt.stream));
+    CG_CUDA(cudaStreamSynchronize(rt.stream));
+    return;
+  }
+  if (v.h == 1 || v.w == 1) {  // a vector: both layouts coincide
+    CG_CUDA(cudaMemcpyAsync(v.buf->ptr, src, n * sizeof(float), cudaMemcpyHostToDevice, rt.stream));
+    CG_CUDA(cudaStreamSynchronize(rt.stream));
+    return;
+  }
+  BufRef staging = DevBuf::alloc(n);
+  CG_CUDA(cudaMemcpyAsync(staging->ptr, src, n * sizeof(float), cudaMemcpyHostToDevice, rt.stream));
+  launch_rowmajor_to_colmajor(staging->ptr, v.buf->ptr, v.h, v.w, rt.stream);
+  rt.launches++;
+  CG_CUDA(cudaStreamSynchronize(rt.stream));
+}
+
+Function* make_matrix_leaf(Kind kind, const char* name, unsigned h, unsigned w, const float* vals) {
+  Value v;
+  v.is_matrix = true;
+  v.h = h;
+  v.w = w;
+  const size_t n = (size_t)h * w;
+  v.buf = DevBuf::alloc(n);
+  // host summary for the identity elimination: all elements equal?
+  v.uniform = n > 0;
+  v.uval = n ? vals[0] : 0.0f;
+  for (size_t i = 1; i < n && v.uniform; i++)
+    if (!(vals[i] == v.uval)) v.uniform = false;
+  if (n && vals[0] != vals[0]) v.uniform = false;  // NaN never equals anything
+  value_upload_rowmajor(v, vals);
+  return new_leaf(kind, name, std::move(v));
+}
+
+Function* make_fill_leaf(Kind kind, const char* name, unsigned h, unsigned w, float x) {
+  // Constant::single_val (constant.rs:30-43): alloc + fill_matrix
+  Runtime& rt = Runtime::get();
+  Value v;
+  v.is_matrix = true;
+  v.h = h;
+  v.w = w;
+  v.uniform = (size_t)h * w > 0 && x == x;
+  v.uval = x;
+  v.buf = DevBuf::alloc((size_t)h * w);
+  fill_device(v.buf->ptr, (size_t)h * w, x);
+  rt.launches++;
+  CG_CUDA(cudaStreamSynchronize(rt.stream));
+  return new_leaf(kind, name, std::move(v));
+}
+
+Function* make_input(const char* name, bool is_matrix, unsigned h, unsigned w) {
+  // Function::input (function.rs:105-108): value = Constant::empty(dims) — uninitialised => undefined
+  Value v;
+  v.is_matrix = is_matrix;
+  v.h = is_matrix ? h : 0;
+  v.w = is_matrix ? w : 0;
+  v.defined = false;
+  v.buf = DevBuf::alloc(v.size());
+  CG_CUDA(cudaMemset(v.buf->ptr, 0, v.size() * sizeof(float)));
+  return new_leaf(Kind::Input, name, std::move(v));
+}
+
+// ---- clone: #[derive(Clone)] (function.rs:10-16) + Matrix::clone (matrix.rs:100-106) ---------------------
+static Value clone_value(const Value& v) {
+  Value c = v;
+  if (v.buf) {
+    Runtime& rt = Runtime::get();
+    c.buf = DevBuf::alloc(v.size());
+    CG_CUDA(cudaMemcpyAsync(c.buf->ptr, v.buf->ptr, v.size() * sizeof(float), cudaMemcpyDeviceToDevice, rt.stream));
+    CG_CUDA(cudaStreamSynchronize(rt.stream));
+  }
+  return c;
+}
+// Non-leaf nodes only need the *summary* of their (stale) initial value: it is never read by the loop
+// (forward overwrites it before any use), only by later identity checks.
+static Value summary_of(const Value& v) {
+  Value c = v;
+  c.buf.reset();
+  return c;
+}
+
+Function* clone_function(const Function& f) {
+  auto* g = new Function();
+  g->value = clone_value(f.value);
+  g->has_params = f.has_params;
+  g->body = f.body;
+  return g;
+}
+
+// ---- value predicates ------------------------------------------------------------------------------------
+static bool device_cmp(bool less, const Value& v, float x) {
+  Runtime& rt = Runtime::get();
+  if (!v.buf) throw Error("value has not been evaluated yet");
+  if (less) launch_all_less_than(v.buf->ptr, v.size(), x, rt.flag, rt.stream);
+  else launch_all_equal(v.buf->ptr, v.size(), x, rt.flag, rt.stream);
+  rt.launches++;
+  int violation = 0;
+  CG_CUDA(cudaMemcpyAsync(&violation, rt.flag, sizeof(int), cudaMemcpyDeviceToHost, rt.stream));
+  CG_CUDA(cudaStreamSynchronize(rt.stream));
+  return violation == 0;
+}
+
+bool value_all_equal(const Value& v, float x) {
+  if (!v.defined) return false;
+  if (v.summary_valid) return v.uniform && v.uval == x;
+  return device_cmp(false, v, x);
+}
+bool value_all_less_than(const Value& v, float x) {
+  if (v.summary_valid && v.uniform) return v.uval < x;
+  return device_cmp(true, v, x);
+}
+void value_download(const Value& v, float* dst) {
+  Runtime& rt = Runtime::get();
+  if (!v.buf) throw Error("value has not been evaluated yet");
+  CG_CUDA(cudaMemcpyAsync(dst, v.buf->ptr, v.size() * sizeof(float), cudaMemcpyDeviceToHost, rt.stream));
+  CG_CUDA(cudaStreamSynchronize(rt.stream));
+}
+
+// ---- op constructors ---------------------------------------------------------------------------------------
+static float unary_identity(Kind k) { return k == Kind::Sigmoid ? 0.5f : 0.0f; }  // ops.rs:331-336,366
+
+Function* make_unary(Kind kind, const Function& f) {
+  // Function1! with identity (ops.rs:45-53): `if f.all_equal(identity) { f.clone() }`
+  if (value_all_equal(f.value, unary_identity(kind))) return clone_function(f);
+  auto* g = new Function();
+  g->value = summary_of(f.value);  // `$f.value().clone()` (ops.rs:39)
+  g->has_params = f.has_params;
+  g->body = std::make_shared<Expr>();
+  g->body->kind = kind;
+  g->body->f1.reset(clone_function(f));
+  return g;
+}
+
+static Function* fold_constant(Function* g);
+
+Function* make_binary(Kind kind, const Function& a, const Function& b) {
+  const float identity = kind == Kind::Mul ? 1.0f : 0.0f;  // ops.rs:338-343 (Sub shares Add's rule, Q4)
+  if (value_all_equal(a.value, identity)) return clone_function(b);  // ops.rs:255-259
+  if (value_all_equal(b.value, identity)) return clone_function(a);
+  auto* g = new Function();
+  // value-shape rule, ops.rs:218-228
+  const Value &va = a.value, &vb = b.value;
+  if (va.is_matrix && vb.is_matrix && (va.h != vb.h || va.w != vb.w)) {
+    delete g;
+    throw Error("assertion failed: m1.dims() == m2.dims()");
+  }
+  g->value = summary_of((!va.is_matrix && vb.is_matrix) ? vb : va);
+  g->has_params = a.has_params || b.has_params;
+  g->body = std::make_shared<Expr>();
+  g->body->kind = kind;
+  g->body->f1.reset(clone_function(a));
+  g->body->f2.reset(clone_function(b));
+  if (a.body->kind == Kind::Constant && b.body->kind == Kind::Constant) return fold_constant(g);
+  return g;
+}
+
+Function* make_dot(const Function& a, bool t1, const Function& b, bool t2) {
+  if (!a.value.is_matrix || !b.value.is_matrix) throw Error("dot should not be used with scalars");  // ops.rs:420
+  const unsigned inner1 = t1 ? a.value.h : a.value.w, inner2 = t2 ? b.value.w : b.value.h;
+  if (inner1 != inner2) throw Error("inner_dim must equal height2");  // cpu/ops.cpp:98
+  auto* g = new Function();
+  g->value.is_matrix = true;  // Matrix::empty_for_dot (matrix.rs:68-83)
+  g->value.h = t1 ? a.value.w : a.value.h;
+  g->value.w = t2 ? b.value.h : b.value.w;
+  g->value.defined = false;  // uninitialised in the reference
+  g->has_params = a.has_params || b.has_params;
+  g->body = std::make_shared<Expr>();
+  g->body->kind = Kind::Dot;
+  g->body->t1 = t1;
+  g->body->t2 = t2;
+  g->body->f1.reset(clone_function(a));
+  g->body->f2.reset(clone_function(b));
+  if (a.body->kind == Kind::Constant && b.body->kind == Kind::Constant) return fold_constant(g);  // ops.rs:398-400
+  return g;
+}
+
+// const (+) const folding (ops.rs:209-213). The reference folds through `eval`, whose
+// `Constant (+) Constant` computes `empty (+) rhs` (Q9, a bug); we fold the mathematics, on the device.
+static Function* fold_constant(Function* g) {
+  std::unique_ptr<Function> node(g);
+  minimize(*node, {}, 0.0f, 1, 2, nullptr, true);  // one forward pass; no params => backward is empty
+  auto* c = new Function();
+  c->value = clone_value(node->value);
+  c->value.defined = true;
+  c->value.summary_valid = false;
+  c->has_params = false;
+  c->body = std::make_shared<Expr>();
+  c->body->kind = Kind::Constant;
+  return c;
+}
+
+// Param leaves in memoised post-order (children f1 then f2); every use site is its own leaf (Q1).
+static void collect(Function& f, std::unordered_set<const Expr*>& seen, std::vector<Function*>& out) {
+  Expr& e = *f.body;
+  if (e.kind == Kind::Param) {
+    out.push_back(&f);
+    return;
+  }
+  if (is_leaf(e.kind)) return;
+  if (!seen.insert(&e).second) return;
+  if (e.f1) collect(*e.f1, seen, out);
+  if (e.f2) collect(*e.f2, seen, out);
+}
+std::vector<Function*> collect_param_leaves(Function& root) {
+  std::unordered_set<const Expr*> seen;
+  std::vector<Function*> out;
+  collect(root, seen, out);
+  return out;
+}
+
+}  // namespace cg

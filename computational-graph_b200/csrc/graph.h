@@ -1,0 +1,113 @@
+// graph.h — host-side graph types mirroring the reference's Rust host (src/function.rs, src/constant.rs).
+//
+//   Value     <-> `Constant` (constant.rs:5-8) held on the device: a matrix is column-major f32 in HBM,
+//                 a scalar is a 1-element device buffer (so whole iterations are CUDA-graph capturable).
+//   Function  <-> `struct Function {value, params, body: Rc<Expr>, pool}` (function.rs:10-16); `clone`
+//                 deep-copies the value and shares the body (Q1: every use site of a param owns a copy).
+//   Expr      <-> `enum Expr` (function.rs:18-33); children are owned by value.
+// The per-node matrix object pool (function.rs:7-8,58-76) is not a member: placeholders are sized and
+// placed by the tape compiler (plan.cpp) inside one device arena, with zero allocations in the loop.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cg_common.h"
+
+namespace cg {
+
+struct DevBuf {
+  float* ptr = nullptr;
+  size_t n = 0;
+  std::shared_ptr<void> keepalive;  // arena that owns `ptr`, when not owned here
+  bool owned = false;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf();
+  static std::shared_ptr<DevBuf> alloc(size_t n);
+};
+using BufRef = std::shared_ptr<DevBuf>;
+
+struct Value {
+  bool is_matrix = false;
+  unsigned h = 0, w = 0;
+  // Oracle rule: values of Dot/Input nodes are uninitialised memory in the reference;
+  // they are "undefined" and never match an identity in the construction-time elimination (Q4).
+  bool defined = true;
+  // Host-side summary used by the value-based identity elimination (ops.rs:45-53,255-263): valid until
+  // the device overwrites the buffer (minimize), after which all_equal runs a device reduction.
+  bool summary_valid = true;
+  bool uniform = false;
+  float uval = 0.0f;
+  BufRef buf;  // device storage: always present for leaves, attached by the plan for evaluated nodes
+  size_t size() const { return is_matrix ? (size_t)h * w : 1; }
+};
+
+enum class Kind { Constant, Input, Param, Neg, Sq, Abs, Signum, Sigmoid, Tanh, Add, Sub, Mul, Dot };
+
+struct Expr;
+struct Plan;
+
+struct Function {
+  Value value;
+  bool has_params = false;  // !params.is_empty() (function.rs:12; Input names count, function.rs:107)
+  std::shared_ptr<Expr> body;
+  std::shared_ptr<Plan> plan;  // compiled tape, cached on the root the user optimises
+  int plan_mode = -1;
+};
+
+struct Expr {
+  Kind kind;
+  std::string name;
+  std::unique_ptr<Function> f1, f2;
+  bool t1 = false, t2 = false;
+};
+
+inline bool is_leaf(Kind k) { return k == Kind::Constant || k == Kind::Input || k == Kind::Param; }
+
+// ---- global runtime state -----------------------------------------------------------------------
+struct Runtime {
+  cudaStream_t stream = nullptr;
+  int mode = 0;          // 0 = exact (the reference's tree walk), 1 = dag (memoised)
+  int tf32 = 0;          // 0 = FP32 SIMT products, 1 = tcgen05 TF32 where eligible
+  int fix_act_grad = 0;  // 0 = reproduce Q3
+  int fuse = 1;          // 0 = one kernel per IR instruction (debug / ablation)
+  int use_graph = 1;     // capture each iteration as a CUDA graph
+  int dp_epoch = 0;      // bumped whenever the data-parallel configuration changes (invalidates plans)
+  int strict_gemm_max = 64;  // products with max(m,n,k) <= this use the bit-exact strict kernel
+  unsigned long long launches = 0;  // kernels launched by this library (bench.py's gpu_launches)
+  int* flag = nullptr;   // device int for all_equal / all_less_than
+  float* red_ws = nullptr;
+  static Runtime& get();
+  void init();
+};
+
+// ---- constructors (function.rs:100-155, ops.rs:36-54,199-264,395-407) --------------------------------
+Function* make_scalar_leaf(Kind kind, const char* name, float v);
+Function* make_matrix_leaf(Kind kind, const char* name, unsigned h, unsigned w, const float* rowmajor_vals);
+Function* make_fill_leaf(Kind kind, const char* name, unsigned h, unsigned w, float v);
+Function* make_input(const char* name, bool is_matrix, unsigned h, unsigned w);
+Function* clone_function(const Function& f);
+Function* make_unary(Kind kind, const Function& f);
+Function* make_binary(Kind kind, const Function& a, const Function& b);
+Function* make_dot(const Function& a, bool t1, const Function& b, bool t2);
+
+bool value_all_equal(const Value& v, float x);
+bool value_all_less_than(const Value& v, float x);
+void value_download(const Value& v, float* dst);  // storage (column-major) order, as get_array
+void value_upload_rowmajor(Value& v, const float* src_rowmajor);
+
+struct Arg {
+  std::string name;
+  const float* vals;  // row-major host floats (matrix) or one float (scalar)
+  unsigned h, w;      // 0,0 for a scalar
+};
+
+// optimize.rs:59-81
+// reuse_inputs: keep the Input values uploaded by an earlier call (device-resident replays).
+void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, int print_freq, float* trace,
+              bool synchronize, bool reuse_inputs = false);
+std::vector<Function*> collect_param_leaves(Function& root);
+
+}  // namespace cg

@@ -1,0 +1,809 @@
+// plan.cpp — tape compiler: Function tree -> SSA tape -> fused steps -> device arena -> CUDA graph.
+//
+// The walker restates src/optimize.rs:84-204 (assign_values / backprop) and the Constant dispatch
+// tables of src/ops.rs:61-158 as *emitters*: instead of computing, each rule appends micro-ops.
+//   exact mode: forward memoised per shared body (pure => bit-identical to the reference's
+//               re-evaluation), backward = the literal pre-order tree walk, one tape segment per
+//               root->node path, leaf SGD emitted where the walk reaches the leaf (Q2).
+//   dag mode  : backward visits every unique node once in reverse topological order, summing the
+//               contributions of its consumers in consumer-visit order (SURVEY §8 mode table).
+#include "tape.h"
+
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <unordered_set>
+
+namespace cg {
+
+Plan::~Plan() {
+  if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  if (graph) cudaGraphDestroy(graph);
+}
+
+namespace {
+
+enum UOp { U_NEG, U_SQ, U_ABS, U_SIGNUM, U_SIGMOID, U_TANH, U_ONE_MINUS };
+enum BOp { B_ADD, B_SUB, B_MUL };
+
+[[noreturn]] void panic(const char* msg) { throw Error(std::string("panic: ") + msg); }
+[[noreturn]] void check_fail(const char* msg) { throw Error(std::string("ERROR: ") + msg); }  // cpu/util.cpp:5-10
+
+bool unary_nonlinear(UOp op) { return op == U_SQ || op == U_ABS || op == U_SIGNUM || op == U_SIGMOID || op == U_TANH; }
+
+struct Builder {
+  Plan& p;
+  float lr;
+  int fix_act_grad;
+  std::unordered_map<const Function*, int> leaf_cur;  // leaf use site -> current SSA version
+  std::unordered_map<const Expr*, int> node_val;      // shared body -> forward value
+  std::unordered_set<const Function*> seen_inputs, seen_params;
+
+  Builder(Plan& plan, float lr_, int fix) : p(plan), lr(lr_), fix_act_grad(fix) {}
+
+  static Shape shape_of(const Function& f) { return Shape{f.value.is_matrix, f.value.h, f.value.w}; }
+
+  int new_val(const Shape& sh) {
+    Val v;
+    v.sh = sh;
+    p.vals.push_back(std::move(v));
+    return (int)p.vals.size() - 1;
+  }
+  int new_fixed(const Shape& sh, const BufRef& buf) {
+    int id = new_val(sh);
+    p.vals[id].fixed = buf->ptr;
+    p.vals[id].keep = buf;
+    p.vals[id].persistent = true;
+    return id;
+  }
+  Shape sh(int v) const { return p.vals[v].sh; }  // by value: emitting grows p.vals
+
+  int emit(IOp op, const Shape& dsh, int a = -1, int b = -1, float imm = 0.0f) {
+    Instr i;
+    i.op = op;
+    i.dst = new_val(dsh);
+    i.a = a;
+    i.b = b;
+    i.imm = imm;
+    p.tape.push_back(i);
+    return i.dst;
+  }
+
+  // ---- leaves ------------------------------------------------------------------------------------------
+  int leaf_val(Function& f) {
+    auto it = leaf_cur.find(&f);
+    if (it != leaf_cur.end()) return it->second;
+    if (!f.value.buf) throw Error("leaf without device storage");
+    int id = new_fixed(shape_of(f), f.value.buf);
+    leaf_cur[&f] = id;
+    if (f.body->kind == Kind::Input && seen_inputs.insert(&f).second) p.input_leaves.push_back(&f);
+    if (f.body->kind == Kind::Param && seen_params.insert(&f).second) p.param_leaves.push_back(&f);
+    return id;
+  }
+  // `value!(f)`: the cached forward value of a child (macros.rs:43-49)
+  int read(Function& f) {
+    if (is_leaf(f.body->kind)) return leaf_val(f);
+    auto it = node_val.find(f.body.get());
+    if (it == node_val.end()) throw Error("internal: node read before evaluation");
+    return it->second;
+  }
+
+  // ---- Constant dispatch tables as emitters ---------------------------------------------------------------
+  int avg(int a) { return sh(a).m ? emit(IOp::Avg, Shape{}, a) : a; }  // ops.rs:430-442
+
+  static IOp unary_iop(UOp op, bool matrix_semantics) {
+    switch (op) {
+      case U_NEG: return IOp::Neg;
+      case U_SQ: return IOp::Sq;
+      case U_ABS: return matrix_semantics ? IOp::AbsM : IOp::AbsS;  // Q8
+      case U_SIGNUM: return matrix_semantics ? IOp::SgnM : IOp::SgnS;
+      case U_SIGMOID: return IOp::Sigmoid;
+      case U_TANH: return IOp::Tanh;
+      case U_ONE_MINUS: return IOp::OneMinus;
+    }
+    return IOp::Neg;
+  }
+  static IOp binary_iop(BOp op) { return op == B_ADD ? IOp::Add : op == B_SUB ? IOp::Sub : IOp::Mul; }
+
+  void check_dims(const Shape& a, const Shape& b, const char* msg) {
+    if (a.m && b.m && (a.h != b.h || a.w != b.w)) check_fail(msg);
+  }
+
+  // Constant1!(linear|nonlinear: op, result, arg) — ops.rs:70-99
+  int equals_unary(UOp op, const Shape& r, int a) {
+    const Shape as = sh(a);
+    if (unary_nonlinear(op) && !r.m && as.m)
+      panic("The result of this operation yields a matrix. Can't place a matrix result in a scalar");
+    if (!r.m && as.m) return emit(unary_iop(op, false), r, avg(a));                 // f(avg(m))
+    if (r.m && as.m) check_dims(r, as, "m->height must equal result->height");
+    return emit(unary_iop(op, r.m && as.m), r, a);  // (S,S) closure | (M,S) fill(f(x)) | (M,M) map_*
+  }
+  // Constant1!(op, c) in place — ops.rs:62-68
+  int assign_unary(UOp op, int c) { return emit(unary_iop(op, sh(c).m), sh(c), c); }
+  // Constant2!(op, result, other): result op= other — ops.rs:102-116
+  int op_assign(BOp op, int r, int o, int dst = -1) {
+    const Shape rs = sh(r);
+    int rhs = (!rs.m && sh(o).m) ? avg(o) : o;
+    if (rs.m && sh(o).m) check_dims(rs, sh(o), "m1->height must equal m2->height");
+    if (dst < 0) return emit(binary_iop(op), rs, r, rhs);
+    Instr i;
+    i.op = binary_iop(op);
+    i.dst = dst;
+    i.a = r;
+    i.b = rhs;
+    p.tape.push_back(i);
+    return dst;
+  }
+  int mul_imm(int r, float s) { return emit(IOp::MulI, sh(r), r, -1, s); }  // `r *= Constant::Scalar(s)`
+  // Constant2!(op, result, c1, c2) — ops.rs:118-148
+  int equals_bin(BOp op, const Shape& r, int a, int b) {
+    if (!r.m) return emit(binary_iop(op), r, avg(a), avg(b));
+    if (sh(a).m) check_dims(r, sh(a), "m1->height must equal result->height");
+    if (sh(b).m) check_dims(r, sh(b), "m2->height must equal result->height");
+    return emit(binary_iop(op), r, a, b);  // fill | broadcast | broadcast_rev | elemwise
+  }
+  // Constant::absorb — constant.rs:106-113. Values are immutable here, so a same-kind copy is an alias.
+  int absorb(const Shape& r, int o) {
+    const Shape os = sh(o);
+    if (!r.m && os.m) return avg(o);
+    if (r.m && !os.m) return emit(IOp::Copy, r, o);  // fill_matrix(scalar)
+    if (r.m) check_dims(r, os, "copy_matrix: dims differ");
+    return o;
+  }
+  // Constant::equals_dot — ops.rs:411-422 + cpu/ops.cpp:88-116 shape checks (generalised, Q7)
+  int equals_dot(const Shape& r, int a, bool t1, int b, bool t2) {
+    const Shape as = sh(a), bs = sh(b);
+    if (!(r.m && as.m && bs.m)) panic("dot should not be used with scalars");
+    const unsigned h1 = t1 ? as.w : as.h, inner = t1 ? as.h : as.w;
+    const unsigned h2 = t2 ? bs.w : bs.h, w2 = t2 ? bs.h : bs.w;
+    if (h1 != r.h) check_fail("height1 must equal result->height");
+    if (inner != h2) check_fail("inner_dim must equal height2");
+    if (w2 != r.w) check_fail("width2 must equal result->width");
+    Instr i;
+    i.op = IOp::Gemm;
+    i.dst = new_val(r);
+    i.a = a;
+    i.b = b;
+    i.ta = t1;
+    i.tb = t2;
+    p.tape.push_back(i);
+    return i.dst;
+  }
+
+  // ---- forward: assign_values, optimize.rs:84-138, memoised per shared body ----------------------------------
+  std::vector<Function*> order;  // first-evaluation (post-)order of the non-leaf nodes
+
+  void forward(Function& f) {
+    Expr& e = *f.body;
+    if (is_leaf(e.kind)) {
+      leaf_val(f);
+      return;
+    }
+    if (node_val.count(&e)) return;
+    if (e.f1) forward(*e.f1);
+    if (e.f2) forward(*e.f2);
+    const Shape r = shape_of(f);
+    int v = -1;
+    switch (e.kind) {
+      case Kind::Neg: v = equals_unary(U_NEG, r, read(*e.f1)); break;
+      case Kind::Sq: v = equals_unary(U_SQ, r, read(*e.f1)); break;
+      case Kind::Abs: v = equals_unary(U_ABS, r, read(*e.f1)); break;
+      case Kind::Signum: v = equals_unary(U_SIGNUM, r, read(*e.f1)); break;
+      case Kind::Sigmoid: v = equals_unary(U_SIGMOID, r, read(*e.f1)); break;
+      case Kind::Tanh: v = equals_unary(U_TANH, r, read(*e.f1)); break;
+      case Kind::Add: v = equals_bin(B_ADD, r, read(*e.f1), read(*e.f2)); break;
+      case Kind::Sub: v = equals_bin(B_SUB, r, read(*e.f1), read(*e.f2)); break;
+      case Kind::Mul: v = equals_bin(B_MUL, r, read(*e.f1), read(*e.f2)); break;
+      case Kind::Dot: v = equals_dot(r, read(*e.f1), e.t1, read(*e.f2), e.t2); break;
+      default: throw Error("internal: unexpected node kind");
+    }
+    node_val[&e] = v;
+    order.push_back(&f);
+  }
+
+  // ---- Param arm of backprop, optimize.rs:149-152 ----------------------------------------------------------------
+  void sgd_leaf(Function& f, int error) {
+    int e2 = mul_imm(error, lr);                  // *error *= Constant::Scalar(learn_rate)
+    int cur = leaf_val(f);
+    int nv = new_fixed(sh(cur), f.value.buf);     // next version lives in the same leaf buffer
+    op_assign(B_SUB, cur, e2, nv);                // self.value -= error   (scalar -= matrix uses avg, Q5)
+    leaf_cur[&f] = nv;
+  }
+
+  // One node's backward rule (optimize.rs:153-200). Returns the errors handed to f1 / f2.
+  void node_backward(Function& f, int error, int& to_f1, int& to_f2) {
+    Expr& e = *f.body;
+    const Shape r = shape_of(f);  // placeholders are shaped like the node's value (function.rs:87-98)
+    to_f1 = to_f2 = -1;
+    switch (e.kind) {
+      case Kind::Neg: to_f1 = assign_unary(U_NEG, error); break;
+      case Kind::Sq: {
+        int t = mul_imm(error, 2.0f);
+        to_f1 = op_assign(B_MUL, t, read(*e.f1));
+      } break;
+      case Kind::Abs: {
+        int ph = equals_unary(U_SIGNUM, r, read(*e.f1));
+        to_f1 = op_assign(B_MUL, ph, error);
+      } break;
+      case Kind::Signum: panic("sign is not differentiable");
+      case Kind::Sigmoid: {
+        int v = read(f);
+        int ph = equals_unary(U_ONE_MINUS, r, v);
+        ph = op_assign(B_MUL, ph, v);
+        // Q3: the child receives the local derivative; `error *= ph` is dead (optimize.rs:168-173)
+        to_f1 = fix_act_grad ? op_assign(B_MUL, error, ph) : ph;
+      } break;
+      case Kind::Tanh: {
+        int v = read(f);
+        int ph = equals_unary(U_SQ, r, v);
+        ph = assign_unary(U_ONE_MINUS, ph);
+        to_f1 = fix_act_grad ? op_assign(B_MUL, error, ph) : ph;
+      } break;
+      case Kind::Add:
+        to_f2 = absorb(r, error);
+        to_f1 = error;
+        break;
+      case Kind::Sub:
+        to_f2 = equals_unary(U_NEG, r, error);
+        to_f1 = error;
+        break;
+      case Kind::Mul:
+        to_f2 = equals_bin(B_MUL, r, read(*e.f1), error);
+        to_f1 = op_assign(B_MUL, error, read(*e.f2));
+        break;
+      case Kind::Dot:
+        // placeholders sized for the gradients they hold (dims of f1 / f2); the reference sizes both like
+        // the result (ops.rs:405), which coincides for its square-only products (Q7)
+        to_f1 = equals_dot(shape_of(*e.f1), error, false, read(*e.f2), !e.t2);
+        to_f2 = equals_dot(shape_of(*e.f2), read(*e.f1), !e.t1, error, false);
+        break;
+      default: break;
+    }
+  }
+
+  // exact mode: the literal pre-order recursion of optimize.rs:140-204
+  void backprop_tree(Function& f, int error) {
+    if (!f.has_params) return;  // :147
+    Expr& e = *f.body;
+    if (e.kind == Kind::Param) return sgd_leaf(f, error);
+    if (is_leaf(e.kind)) return;
+    int e1, e2;
+    node_backward(f, error, e1, e2);
+    if (e.f1) backprop_tree(*e.f1, e1);
+    if (e.f2) backprop_tree(*e.f2, e2);
+  }
+
+  // dag mode
+  std::unordered_map<const Expr*, int> node_err;
+  void dag_deliver(Function& child, int g) {
+    if (!child.has_params) return;
+    Expr& ce = *child.body;
+    if (ce.kind == Kind::Param) return sgd_leaf(child, g);
+    if (is_leaf(ce.kind)) return;
+    auto it = node_err.find(&ce);
+    if (it == node_err.end()) node_err[&ce] = g;           // first contribution
+    else it->second = op_assign(B_ADD, it->second, g);     // f32 sum in consumer-visit order
+  }
+  void backprop_dag(Function& root, int error) {
+    if (!root.has_params) return;
+    Expr& re = *root.body;
+    if (re.kind == Kind::Param) return sgd_leaf(root, error);
+    if (is_leaf(re.kind)) return;
+    node_err[&re] = error;
+    for (int idx = (int)order.size() - 1; idx >= 0; idx--) {
+      Function& f = *order[idx];
+      auto it = node_err.find(f.body.get());
+      if (it == node_err.end()) continue;
+      if (f.has_params) {
+        int e1, e2;
+        node_backward(f, it->second, e1, e2);
+        Expr& e = *f.body;
+        if (e.f1) dag_deliver(*e.f1, e1);
+        if (e.f2) dag_deliver(*e.f2, e2);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// passes
+// ------------------------------------------------------------------------------------------------------
+void for_each_use(const Instr& i, const std::function<void(int)>& fn) {
+  if (i.a >= 0) fn(i.a);
+  if (i.b >= 0) fn(i.b);
+  if (i.c_in >= 0) fn(i.c_in);
+}
+
+void dead_code_elimination(Plan& p) {
+  std::vector<char> live(p.vals.size(), 0);
+  for (size_t v = 0; v < p.vals.size(); v++) live[v] = p.vals[v].persistent;
+  for (int k = (int)p.tape.size() - 1; k >= 0; k--) {
+    Instr& i = p.tape[k];
+    if (!live[i.dst]) {
+      i.dead = true;
+      continue;
+    }
+    for_each_use(i, [&](int v) { live[v] = 1; });
+  }
+}
+
+void count_uses(Plan& p) {
+  for (auto& v : p.vals) v.nuses = 0;
+  for (auto& i : p.tape)
+    if (!i.dead) for_each_use(i, [&](int v) { p.vals[v].nuses++; });
+}
+
+// dW product + SGD update:  g = A^T.E ; e = g * lr ; W' = W - e   ==>   W' = W - (A^T.E) * lr in the gemm
+// epilogue (two roundings, as the reference: optimize.rs:149-152). The update is hoisted to the gemm's
+// position, which is legal when nothing in between reads the old version of W.
+void fuse_gemm_sgd(Plan& p) {
+  count_uses(p);
+  std::vector<int> user(p.vals.size(), -1);  // the single user of a value (valid when nuses == 1)
+  for (size_t k = 0; k < p.tape.size(); k++)
+    if (!p.tape[k].dead) for_each_use(p.tape[k], [&](int v) { user[v] = (int)k; });
+  for (size_t k = 0; k < p.tape.size(); k++) {
+    Instr& g = p.tape[k];
+    if (g.dead || g.op != IOp::Gemm || g.epi != 0) continue;
+    Val& gv = p.vals[g.dst];
+    if (gv.persistent || gv.nuses != 1) continue;
+    Instr& mu = p.tape[user[g.dst]];
+    if (mu.op != IOp::MulI || mu.a != g.dst || p.vals[mu.dst].nuses != 1 || p.vals[mu.dst].persistent) continue;
+    const int sub_idx = user[mu.dst];
+    Instr& sb = p.tape[sub_idx];
+    if (sb.op != IOp::Sub || sb.b != mu.dst || sb.a == mu.dst) continue;
+    const Val &oldv = p.vals[sb.a], &newv = p.vals[sb.dst];
+    if (!oldv.fixed || oldv.fixed != newv.fixed || !oldv.sh.same(gv.sh) || !gv.sh.m) continue;
+    bool blocked = false;
+    for (int q = (int)k + 1; q < sub_idx && !blocked; q++) {
+      const Instr& o = p.tape[q];
+      if (o.dead) continue;
+      for_each_use(o, [&](int v) {
+        if (p.vals[v].fixed == oldv.fixed) blocked = true;  // someone still reads (a version of) this leaf
+      });
+      if (p.vals[o.dst].fixed == oldv.fixed) blocked = true;
+    }
+    if (blocked) continue;
+    g.epi = 1;
+    g.c_in = sb.a;
+    g.imm = mu.imm;
+    g.dst = sb.dst;
+    mu.dead = true;
+    sb.dead = true;
+    p.stats.gemms_fused_sgd++;
+  }
+  count_uses(p);
+}
+
+// dX accumulation in dag mode:  g = E.W^T ; err' = err + g  ==>  err' = err + E.W^T in the gemm epilogue.
+void fuse_gemm_accumulate(Plan& p) {
+  count_uses(p);
+  std::vector<int> user(p.vals.size(), -1), def_idx(p.vals.size(), -1);
+  for (size_t k = 0; k < p.tape.size(); k++)
+    if (!p.tape[k].dead) {
+      for_each_use(p.tape[k], [&](int v) { user[v] = (int)k; });
+      def_idx[p.tape[k].dst] = (int)k;
+    }
+  for (size_t k = 0; k < p.tape.size(); k++) {
+    Instr& g = p.tape[k];
+    if (g.dead || g.op != IOp::Gemm || g.epi != 0) continue;
+    Val& gv = p.vals[g.dst];
+    if (gv.persistent || gv.nuses != 1) continue;
+    const int add_idx = user[g.dst];
+    Instr& ad = p.tape[add_idx];
+    if (ad.op != IOp::Add || ad.b != g.dst || ad.a == g.dst) continue;
+    Val& acc = p.vals[ad.a];
+    if (acc.fixed || acc.persistent || acc.nuses != 1 || !acc.sh.same(gv.sh) || p.vals[ad.dst].persistent) continue;
+    // the accumulator must already exist when the gemm runs: its definition precedes the gemm
+    if (def_idx[ad.a] < 0 || def_idx[ad.a] >= (int)k || ad.a == g.a || ad.a == g.b) continue;
+    g.epi = 2;
+    g.c_in = ad.a;
+    g.dst = ad.dst;
+    p.vals[ad.dst].alias_of = ad.a;
+    ad.dead = true;
+  }
+  count_uses(p);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Elementwise fusion: compile tape[s, e) into one register-bytecode program, or fail.
+// ------------------------------------------------------------------------------------------------------
+struct GroupCompiler {
+  const Plan& p;
+  const std::vector<int>& last_use_idx;  // tape index of the last live use of each value (-1: none)
+  GroupCompiler(const Plan& plan, const std::vector<int>& lu) : p(plan), last_use_idx(lu) {}
+
+  static EwOpcode opcode(IOp op) {
+    switch (op) {
+      case IOp::Neg: return OP_NEG;
+      case IOp::Sq: return OP_SQ;
+      case IOp::AbsM: return OP_ABS_M;
+      case IOp::SgnM: return OP_SGN_M;
+      case IOp::AbsS: return OP_ABS_S;
+      case IOp::SgnS: return OP_SGN_S;
+      case IOp::Sigmoid: return OP_SIGMOID;
+      case IOp::Tanh: return OP_TANH;
+      case IOp::OneMinus: return OP_ONE_MINUS;
+      case IOp::Add: return OP_ADD;
+      case IOp::Sub: return OP_SUB;
+      case IOp::Mul: return OP_MUL;
+      default: return OP_END;
+    }
+  }
+
+  bool compile(const std::vector<int>& idx, EwGroup& g) const {
+    // idx: tape indices (live, elementwise, same domain) in order
+    g = EwGroup();
+    const Instr& first = p.tape[idx[0]];
+    g.n = p.vals[first.dst].sh.n();
+    std::unordered_map<int, int> reg;       // value -> register
+    std::unordered_map<int, int> uses_left; // in-group uses remaining
+    std::unordered_set<int> defined;
+    const int group_end = idx.back();
+    for (int k : idx) {
+      const Instr& i = p.tape[k];
+      for_each_use(i, [&](int v) { uses_left[v]++; });
+    }
+    // inputs: used before defined in the group, in order of first use
+    {
+      std::unordered_set<int> def;
+      for (int k : idx) {
+        const Instr& i = p.tape[k];
+        for_each_use(i, [&](int v) {
+          if (!def.count(v) && !reg.count(v)) {
+            reg[v] = (int)g.in.size();
+            g.in.push_back(v);
+          }
+        });
+        def.insert(i.dst);
+      }
+    }
+    if (g.in.size() > (size_t)EW_MAX_IN) return false;
+    std::vector<char> reg_busy(EW_REGS, 0);
+    for (size_t r = 0; r < g.in.size(); r++) reg_busy[r] = 1;
+    auto alloc_reg = [&]() {
+      for (int r = 0; r < EW_REGS; r++)
+        if (!reg_busy[r]) {
+          reg_busy[r] = 1;
+          return r;
+        }
+      return -1;
+    };
+    auto imm_index = [&](float x) {
+      for (size_t q = 0; q < g.imm.size(); q++)
+        if (memcmp(&g.imm[q], &x, sizeof(float)) == 0) return (int)q;
+      g.imm.push_back(x);
+      return (int)g.imm.size() - 1;
+    };
+    auto release_use = [&](int v) {
+      if (--uses_left[v] == 0) {
+        auto it = reg.find(v);
+        if (it != reg.end()) {
+          reg_busy[it->second] = 0;
+          reg.erase(it);
+        }
+      }
+    };
+    int acc = -1;  // value currently held by the accumulator
+    auto load_acc = [&](int v) -> bool {
+      if (acc == v) return true;
+      auto it = reg.find(v);
+      if (it == reg.end()) return false;
+      g.code.push_back(ew_encode(OP_LDR, it->second));
+      acc = v;
+      return true;
+    };
+    for (size_t q = 0; q < idx.size(); q++) {
+      const Instr& i = p.tape[idx[q]];
+      switch (i.op) {
+        case IOp::Fill: g.code.push_back(ew_encode(OP_LDI, imm_index(i.imm))); break;
+        case IOp::Copy:
+          if (!load_acc(i.a)) return false;
+          release_use(i.a);
+          break;
+        case IOp::MulI: {
+          if (!load_acc(i.a)) return false;
+          int k = imm_index(i.imm);
+          g.code.push_back(ew_encode(OP_MULI, k));
+          release_use(i.a);
+        } break;
+        case IOp::Add: case IOp::Sub: case IOp::Mul: {
+          EwOpcode oc = opcode(i.op);
+          if (i.a == i.b && i.op == IOp::Mul && (acc == i.a || reg.count(i.a))) {
+            if (!load_acc(i.a)) return false;
+            g.code.push_back(ew_encode(OP_SQ));
+          } else if (reg.count(i.b)) {
+            if (!load_acc(i.a)) return false;
+            g.code.push_back(ew_encode(oc, reg[i.b]));
+          } else if (acc == i.b && reg.count(i.a)) {
+            // b lives only in the accumulator: commute, or reverse-subtract
+            g.code.push_back(ew_encode(i.op == IOp::Sub ? OP_RSUB : oc, reg[i.a]));
+          } else {
+            return false;
+          }
+          release_use(i.a);
+          release_use(i.b);
+        } break;
+        default:
+          if (!load_acc(i.a)) return false;
+          g.code.push_back(ew_encode(opcode(i.op)));
+          release_use(i.a);
+          break;
+      }
+      acc = i.dst;
+      if (g.imm.size() > (size_t)EW_MAX_IMM) return false;
+      const Val& dv = p.vals[i.dst];
+      // memory: persistent, or read after the group ends
+      if (dv.persistent || last_use_idx[i.dst] > group_end) {
+        if (g.out.size() >= (size_t)EW_MAX_OUT) return false;
+        g.code.push_back(ew_encode(OP_STG, (int)g.out.size()));
+        g.out.push_back(i.dst);
+      }
+      // register: needed unless the only in-group use is the next instruction's accumulator operand
+      int ul = uses_left.count(i.dst) ? uses_left[i.dst] : 0;
+      if (ul > 0) {
+        bool acc_only = false;
+        if (ul == 1 && q + 1 < idx.size()) {
+          const Instr& nx = p.tape[idx[q + 1]];
+          int cnt = (nx.a == i.dst) + (nx.b == i.dst);
+          if (cnt == 1) {
+            if (nx.a == i.dst) {
+              // first operand: fine when the second (if any) is in a register
+              acc_only = (nx.b < 0) || reg.count(nx.b);
+            } else {
+              acc_only = reg.count(nx.a) > 0;  // commuted / reverse-subtract form
+            }
+          }
+        }
+        if (!acc_only) {
+          int r = alloc_reg();
+          if (r < 0) return false;
+          reg[i.dst] = r;
+          g.code.push_back(ew_encode(OP_STR, r));
+        }
+      }
+      if (g.code.size() > (size_t)EW_MAX_INS) return false;
+    }
+    return !g.code.empty() || !g.out.empty();
+  }
+};
+
+void build_steps(Plan& p) {
+  // last live use of every value, as a tape index
+  std::vector<int> last_use(p.vals.size(), -1);
+  for (size_t k = 0; k < p.tape.size(); k++)
+    if (!p.tape[k].dead) for_each_use(p.tape[k], [&](int v) { last_use[v] = (int)k; });
+  GroupCompiler gc(p, last_use);
+  const size_t max_group = p.fuse ? 96 : 1;
+  size_t k = 0;
+  const size_t N = p.tape.size();
+  while (k < N) {
+    const Instr& i = p.tape[k];
+    if (i.dead) {
+      k++;
+      continue;
+    }
+    p.stats.live_instrs++;
+    if (!is_ew(i.op)) {
+      Step s;
+      s.kind = i.op == IOp::Gemm ? Step::GEMM : i.op == IOp::Avg ? Step::AVG : Step::ALLREDUCE;
+      s.ins = i;
+      p.steps.push_back(std::move(s));
+      k++;
+      continue;
+    }
+    // grow an elementwise group: consecutive live EW instrs with the same domain
+    const Shape dom = p.vals[i.dst].sh;
+    std::vector<int> idx{(int)k};
+    EwGroup best;
+    if (!gc.compile(idx, best)) throw Error("internal: single elementwise instruction does not compile");
+    size_t next = k + 1;
+    while (next < N && idx.size() < max_group) {
+      const Instr& c = p.tape[next];
+      if (c.dead) {
+        next++;
+        continue;
+      }
+      if (!is_ew(c.op) || !p.vals[c.dst].sh.same(dom)) break;
+      idx.push_back((int)next);
+      EwGroup trial;
+      if (!gc.compile(idx, trial)) {
+        idx.pop_back();
+        break;
+      }
+      best = std::move(trial);
+      next++;
+    }
+    p.stats.live_instrs += idx.size() - 1;
+    Step s;
+    s.kind = Step::EW;
+    s.ew = std::move(best);
+    p.steps.push_back(std::move(s));
+    k = (size_t)idx.back() + 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Device arena: every value that crosses a kernel boundary gets a slot; slots are recycled by liveness.
+// ------------------------------------------------------------------------------------------------------
+void step_defs_uses(const Step& s, std::vector<int>& defs, std::vector<int>& uses) {
+  defs.clear();
+  uses.clear();
+  if (s.kind == Step::EW) {
+    defs = s.ew.out;
+    uses = s.ew.in;
+  } else {
+    defs.push_back(s.ins.dst);
+    for_each_use(s.ins, [&](int v) { uses.push_back(v); });
+  }
+}
+
+void assign_memory(Plan& p) {
+  std::vector<int> defs, uses;
+  for (size_t si = 0; si < p.steps.size(); si++) {
+    step_defs_uses(p.steps[si], defs, uses);
+    for (int v : defs) {
+      p.vals[v].def_step = (int)si;
+      p.vals[v].needs_mem = true;
+      if (p.vals[v].last_step < (int)si) p.vals[v].last_step = (int)si;
+    }
+    for (int v : uses) p.vals[v].last_step = (int)si;
+  }
+  // alias chains extend the life of the underlying slot
+  auto root_of = [&](int v) {
+    while (p.vals[v].alias_of >= 0) v = p.vals[v].alias_of;
+    return v;
+  };
+  for (size_t v = 0; v < p.vals.size(); v++)
+    if (p.vals[v].alias_of >= 0 && p.vals[v].needs_mem) {
+      int r = root_of((int)v);
+      p.vals[r].last_step = std::max(p.vals[r].last_step, p.vals[v].last_step);
+    }
+  constexpr size_t ALIGN = 256;
+  std::map<size_t, std::vector<size_t>> free_slots;  // bytes -> offsets
+  std::vector<std::vector<int>> release_at(p.steps.size());
+  size_t top = 0;
+  std::vector<size_t> off(p.vals.size(), SIZE_MAX);
+  for (size_t si = 0; si < p.steps.size(); si++) {
+    step_defs_uses(p.steps[si], defs, uses);
+    for (int v : defs) {
+      Val& val = p.vals[v];
+      if (val.fixed || val.alias_of >= 0) continue;
+      size_t bytes = (val.sh.n() * sizeof(float) + ALIGN - 1) / ALIGN * ALIGN;
+      auto& fl = free_slots[bytes];
+      if (!fl.empty()) {
+        off[v] = fl.back();
+        fl.pop_back();
+      } else {
+        off[v] = top;
+        top += bytes;
+      }
+      release_at[val.last_step].push_back(v);
+    }
+    for (int v : release_at[si]) {
+      size_t bytes = (p.vals[v].sh.n() * sizeof(float) + ALIGN - 1) / ALIGN * ALIGN;
+      free_slots[bytes].push_back(off[v]);
+    }
+  }
+  p.stats.arena_bytes = top;
+  if (top) p.arena = DevBuf::alloc(top / sizeof(float));
+  for (size_t v = 0; v < p.vals.size(); v++) {
+    Val& val = p.vals[v];
+    if (val.fixed) val.ptr = val.fixed;
+    else if (off[v] != SIZE_MAX) val.ptr = p.arena->ptr + off[v] / sizeof(float);
+  }
+  for (size_t v = 0; v < p.vals.size(); v++) {
+    Val& val = p.vals[v];
+    if (!val.fixed && val.alias_of >= 0) val.ptr = p.vals[root_of((int)v)].ptr;
+  }
+}
+
+void finalize_steps(Plan& p) {
+  for (Step& s : p.steps) {
+    if (s.kind == Step::EW) {
+      EwProgram& pr = s.prog;
+      memset(&pr, 0, sizeof pr);
+      pr.n = s.ew.n;
+      pr.n_in = (uint32_t)s.ew.in.size();
+      pr.n_out = (uint32_t)s.ew.out.size();
+      pr.n_ins = (uint32_t)s.ew.code.size();
+      for (size_t k = 0; k < s.ew.in.size(); k++) {
+        const Val& v = p.vals[s.ew.in[k]];
+        if (!v.ptr) throw Error("internal: elementwise input without storage");
+        pr.in[k] = v.ptr;
+        if (!v.sh.m) pr.in_scalar_mask |= 1u << k;  // scalar operand: broadcast
+        if (!(pr.in_scalar_mask >> k & 1u)) p.stats.ew_bytes_per_iter += 4.0 * (double)pr.n;
+      }
+      for (size_t k = 0; k < s.ew.out.size(); k++) {
+        const Val& v = p.vals[s.ew.out[k]];
+        if (!v.ptr) throw Error("internal: elementwise output without storage");
+        pr.out[k] = v.ptr;
+        p.stats.ew_bytes_per_iter += 4.0 * (double)pr.n;
+      }
+      for (size_t k = 0; k < s.ew.imm.size(); k++) pr.imm[k] = s.ew.imm[k];
+      for (size_t k = 0; k < s.ew.code.size(); k++) pr.code[k] = s.ew.code[k];
+      p.stats.ew_groups++;
+    } else if (s.kind == Step::GEMM) {
+      const Shape &as = p.vals[s.ins.a].sh, &cs = p.vals[s.ins.dst].sh;
+      const double k = s.ins.ta ? as.h : as.w;
+      p.stats.gemm_flop_per_iter += 2.0 * cs.h * cs.w * k;
+      p.stats.gemms++;
+    } else if (s.kind == Step::AVG) {
+      p.stats.reduces++;
+    }
+  }
+  p.stats.kernels_per_iter = p.steps.size();
+}
+
+}  // namespace
+
+std::shared_ptr<Plan> build_plan(Function& root, float lr) {
+  Runtime& rt = Runtime::get();
+  auto plan = std::make_shared<Plan>();
+  Plan& p = *plan;
+  p.lr = lr;
+  p.mode = rt.mode;
+  p.tf32 = rt.tf32;
+  p.fix_act_grad = rt.fix_act_grad;
+  p.fuse = rt.fuse;
+  p.dp_epoch = rt.dp_epoch;
+
+  Builder b(p, lr, rt.fix_act_grad);
+  b.forward(root);
+  const Shape rsh = Builder::shape_of(root);
+  p.root_n = rsh.n();
+  int root_val = b.read(root);
+  if (is_leaf(root.body->kind)) {
+    p.root_is_leaf = true;
+    p.root_ptr = root.value.buf->ptr;
+  } else {
+    // the root's cached value must survive the iteration (Q12; print / all_less_than / value readback)
+    if (!root.value.buf || root.value.buf->n != rsh.n()) root.value.buf = DevBuf::alloc(rsh.n());
+    p.vals[root_val].fixed = root.value.buf->ptr;
+    p.vals[root_val].keep = root.value.buf;
+    p.vals[root_val].persistent = true;
+    p.root_ptr = root.value.buf->ptr;
+  }
+  // optimize.rs:69 — `let mut error = self.value_mut().copy_and_fill(1.)`
+  int error = b.emit(IOp::Fill, rsh, -1, -1, 1.0f);
+  if (p.mode == 0) b.backprop_tree(root, error);
+  else b.backprop_dag(root, error);
+
+  p.stats.tape_instrs = p.tape.size();
+  dead_code_elimination(p);
+  if (p.fuse) {
+    fuse_gemm_sgd(p);
+    fuse_gemm_accumulate(p);
+    dead_code_elimination(p);
+  }
+  build_steps(p);
+  assign_memory(p);
+  finalize_steps(p);
+  return plan;
+}
+
+void plan_launch_iteration(Plan& p, cudaStream_t stream) {
+  Runtime& rt = Runtime::get();
+  for (Step& s : p.steps) {
+    switch (s.kind) {
+      case Step::EW: launch_ew_program(s.prog, stream); break;
+      case Step::AVG: {
+        const Val& a = p.vals[s.ins.a];
+        launch_reduce_avg(a.ptr, a.sh.n(), p.vals[s.ins.dst].ptr, rt.red_ws, stream);
+      } break;
+      case Step::GEMM: {
+        const Val &a = p.vals[s.ins.a], &b = p.vals[s.ins.b], &c = p.vals[s.ins.dst];
+        const int m = (int)c.sh.h, n = (int)c.sh.w, k = (int)(s.ins.ta ? a.sh.h : a.sh.w);
+        GemmEpilogue epi;
+        epi.mode = s.ins.epi;
+        epi.lr = s.ins.imm;
+        if (s.ins.epi && p.vals[s.ins.c_in].ptr != c.ptr) throw Error("internal: gemm epilogue operand is not in place");
+        launch_gemm(a.ptr, s.ins.ta, b.ptr, s.ins.tb, c.ptr, m, n, k, (int)a.sh.h, (int)b.sh.h, (int)c.sh.h, epi,
+                    p.tf32 != 0, stream);
+      } break;
+      case Step::ALLREDUCE: dp_allreduce_sum(p.vals[s.ins.dst].ptr, p.vals[s.ins.dst].sh.n(), stream); break;
+    }
+  }
+}
+
+}  // namespace cg

@@ -1,0 +1,99 @@
+// tape.h — the linear IR ("tape") one `minimize` iteration compiles to, and the compiled plan.
+//
+// The reference walks the Function tree recursively every iteration, issuing one FFI call (= one
+// eager kernel) per node (src/optimize.rs:84-204). Here the walk happens ONCE, at minimize() entry:
+// it emits SSA micro-ops over immutable values; the tape is then dead-code-eliminated, the dW product
+// is fused with its SGD update, runs of same-shaped elementwise micro-ops are fused into register
+// bytecode programs (one HBM pass per sub-tree), every surviving value gets a slot in one device
+// arena sized from the tape (zero allocations inside the loop), and the iteration is captured as a
+// CUDA graph.
+#pragma once
+#include <unordered_map>
+#include <vector>
+
+#include "graph.h"
+
+namespace cg {
+
+struct Shape {
+  bool m = false;
+  unsigned h = 0, w = 0;
+  size_t n() const { return m ? (size_t)h * w : 1; }
+  bool same(const Shape& o) const { return m == o.m && (!m || (h == o.h && w == o.w)); }
+};
+
+enum class IOp : uint8_t {
+  // elementwise micro-ops (fusable)
+  Neg, Sq, AbsM, SgnM, AbsS, SgnS, Sigmoid, Tanh, OneMinus, Add, Sub, Mul, MulI, Fill, Copy,
+  // kernel-boundary ops
+  Avg,        // dst(scalar) = reduce_sum(a) / size(a)            (ops.rs:438-442)
+  Gemm,       // dst = op(a) . op(b) [epilogue]                   (ops.rs:411-422)
+  AllReduce,  // dst = sum over data-parallel ranks of a (in place)
+};
+inline bool is_ew(IOp op) { return op <= IOp::Copy; }
+
+struct Val {
+  Shape sh;
+  float* fixed = nullptr;  // storage owned elsewhere (leaf / constant / input / root value buffers)
+  BufRef keep;
+  bool persistent = false;  // must be in memory after the iteration (leaf versions, root value)
+  // planning
+  int nuses = 0;
+  int def_step = -1, last_step = -1;
+  bool needs_mem = false;
+  int alias_of = -1;  // shares memory with this value (in-place update of a temp)
+  float* ptr = nullptr;
+};
+
+struct Instr {
+  IOp op;
+  int dst = -1, a = -1, b = -1;
+  float imm = 0.0f;
+  bool ta = false, tb = false;  // Gemm
+  int epi = 0;                  // Gemm epilogue: 0 store, 1 fused SGD (c_in - acc*imm), 2 accumulate (c_in + acc)
+  int c_in = -1;
+  bool dead = false;
+};
+
+struct EwGroup {
+  size_t n = 0;
+  std::vector<int> in, out;  // value ids
+  std::vector<uint16_t> code;
+  std::vector<float> imm;
+};
+
+struct Step {
+  enum Kind { EW, AVG, GEMM, ALLREDUCE } kind;
+  EwGroup ew;
+  Instr ins;  // AVG / GEMM / ALLREDUCE
+  EwProgram prog;  // EW, filled after memory assignment
+};
+
+struct PlanStats {
+  size_t tape_instrs = 0, live_instrs = 0, ew_groups = 0, gemms = 0, gemms_fused_sgd = 0, reduces = 0;
+  size_t arena_bytes = 0, kernels_per_iter = 0;
+  double gemm_flop_per_iter = 0.0, ew_bytes_per_iter = 0.0;
+};
+
+struct Plan {
+  std::vector<Val> vals;
+  std::vector<Instr> tape;
+  std::vector<Step> steps;
+  BufRef arena;
+  PlanStats stats;
+  float lr = 0.0f;
+  int mode = 0, tf32 = 0, fix_act_grad = 0, fuse = 1, dp_epoch = 0;
+  bool root_is_leaf = false;
+  float* root_ptr = nullptr;
+  size_t root_n = 1;
+  std::vector<Function*> input_leaves;
+  std::vector<Function*> param_leaves;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  ~Plan();
+};
+
+std::shared_ptr<Plan> build_plan(Function& root, float lr);
+void plan_launch_iteration(Plan& p, cudaStream_t stream);  // enqueue the kernels of one iteration
+
+}  // namespace cg

@@ -1,0 +1,108 @@
+/* cg_graph.h — graph-level C ABI of libcg_b200.so: the reference's L4 surface
+ * (Function / ops / minimize) as plain `extern "C"` entry points.
+ *
+ * Why a second boundary besides cg_matrix.h: the reference crosses its FFI once per node per
+ * iteration (one eager kernel per call, src/ops.rs:61-158). Fusing sub-trees into one kernel, a
+ * device-resident pool with zero allocations in the loop, CUDA-graph replay and data-parallel
+ * gradient all-reduce cannot be expressed through per-op calls, so the host layer a Rust shim
+ * (function.rs / ops.rs / optimize.rs re-done as thin wrappers) binds is THIS header.
+ * Each entry point cites the reference interface it replaces. Handles are opaque; every function
+ * that can fail returns NULL / non-zero and leaves a message in cg_last_error() — the message is the
+ * reference's own `panic!` / `check()` text ("panic: …" / "ERROR: …").
+ *
+ * Values: matrices are passed in as ROW-major host floats (what `Constant::matrix(h, w, vals)` takes,
+ * src/matrix.rs:59-66) and stored column-major on the device; read-backs return raw storage order
+ * (column-major), exactly like `get_array`.
+ */
+#ifndef CG_GRAPH_H
+#define CG_GRAPH_H
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cg_function cg_function; /* `struct Function` (src/function.rs:10-16) */
+
+/* ---- leaves: src/function.rs:100-155 ----------------------------------------------------------- */
+cg_function *cg_scalar_param(const char *name, float value);                               /* :115-118 */
+cg_function *cg_matrix_param(const char *name, unsigned h, unsigned w, const float *vals); /* :120-123 */
+cg_function *cg_single_val_param(const char *name, unsigned h, unsigned w, float value);   /* :125-128 */
+cg_function *cg_scalar(float value);                                                       /* :141-144 */
+cg_function *cg_matrix(unsigned h, unsigned w, const float *vals);                         /* :146-149 */
+cg_function *cg_single_val_matrix(unsigned h, unsigned w, float value);                    /* :151-154 */
+cg_function *cg_input(const char *name, int is_matrix, unsigned h, unsigned w);            /* :104-108 */
+cg_function *cg_clone(const cg_function *f);   /* #[derive(Clone)]: deep value copy, shared body (Q1) */
+void cg_release(cg_function *f);               /* Drop */
+
+/* ---- op constructors: src/ops.rs:36-54,199-264,331-343,363-376,395-407 -------------------------
+ * Value-based identity elimination and const folding happen here, as in the reference (Q4). */
+cg_function *cg_neg(const cg_function *f);
+cg_function *cg_sq(const cg_function *f);
+cg_function *cg_abs(const cg_function *f);
+cg_function *cg_signum(const cg_function *f);
+cg_function *cg_sigmoid(const cg_function *f);
+cg_function *cg_tanh(const cg_function *f);
+cg_function *cg_add(const cg_function *a, const cg_function *b);
+cg_function *cg_sub(const cg_function *a, const cg_function *b);
+cg_function *cg_mul(const cg_function *a, const cg_function *b);
+cg_function *cg_dot(const cg_function *a, int trans1, const cg_function *b, int trans2); /* dot!, macros.rs:51-64 */
+
+/* ---- optimisation: src/optimize.rs:59-81 ---------------------------------------------------------
+ * args: `&HashMap<&str, Constant>` flattened — for entry i, arg_vals[i] points at arg_h[i]*arg_w[i]
+ * row-major floats, or one float with arg_h[i] == arg_w[i] == 0 for a scalar.
+ * trace (may be NULL): receives the root value of every iteration (iters * size floats, storage
+ * order) — the value the reference would print, i.e. the forward value BEFORE that iteration's
+ * update (Q12). print_freq <= 0 or > iters: never print. Returns 0 on success. Blocks until done. */
+int cg_minimize(cg_function *f, int nargs, const char **names, const float **arg_vals, const unsigned *arg_h,
+                const unsigned *arg_w, float learn_rate, int iters, int print_freq, float *trace);
+int cg_maximize(cg_function *f, int nargs, const char **names, const float **arg_vals, const unsigned *arg_h,
+                const unsigned *arg_w, float learn_rate, int iters, int print_freq, float *trace);
+/* Same loop, enqueued on the library stream without waiting (device-resident timing: bench.py). */
+int cg_minimize_async(cg_function *f, float learn_rate, int iters);
+int cg_synchronize(void);
+
+/* ---- read-back: Function::value / all_less_than / all_equal (src/ops.rs:309-329) ----------------- */
+int cg_value_dims(const cg_function *f, unsigned *h, unsigned *w); /* returns 1 for a matrix, 0 for a scalar */
+void cg_value_get(const cg_function *f, float *dst);
+bool cg_all_less_than(const cg_function *f, float x);
+bool cg_all_equal(const cg_function *f, float x);
+/* Parameter leaves in memoised post-order; every use site of a param is its own leaf (Q1). */
+int cg_num_leaves(cg_function *f);
+int cg_leaf_info(cg_function *f, int i, char *name, int name_cap, unsigned *h, unsigned *w);
+int cg_leaf_get(cg_function *f, int i, float *dst);
+int cg_leaf_set(cg_function *f, int i, const float *src_rowmajor); /* checkpoint restore */
+int cg_kind(const cg_function *f);
+
+/* ---- execution switches (defaults reproduce the reference; also CG_MODE / CG_TF32 / … env) ------- */
+void cg_set_mode(int mode);           /* 0 = exact (the reference's tree walk), 1 = dag (memoised, visit-once) */
+void cg_set_tf32(int on);             /* 1: tcgen05 TF32 tensor-core products for eligible shapes */
+void cg_set_fix_act_grad(int on);     /* 1: sigmoid/tanh pass error*derivative (repairs Q3) */
+void cg_set_fuse(int on);             /* 0: one kernel per tape instruction (ablation) */
+void cg_set_cuda_graph(int on);       /* 0: launch kernels eagerly instead of replaying a CUDA graph */
+void cg_set_strict_gemm_max(int dim); /* products with max(m,n,k) <= dim use the bit-exact kernel */
+
+/* ---- introspection -------------------------------------------------------------------------------- */
+typedef struct {
+  unsigned long long tape_instrs, live_instrs, kernels_per_iter, ew_kernels, gemms, gemms_fused_sgd, reduces;
+  unsigned long long arena_bytes;
+  double gemm_flop_per_iter, ew_bytes_per_iter;
+} cg_plan_stats;
+int cg_plan_stats_get(cg_function *f, float learn_rate, cg_plan_stats *out); /* compiles the plan if needed */
+unsigned long long cg_launch_count(void); /* kernels launched by this library so far */
+const char *cg_last_error(void);
+/* Times `reps` replays of f's iteration with CUDA events on the library stream; returns ms per iteration. */
+double cg_time_iterations(cg_function *f, float learn_rate, int warmup, int reps);
+
+/* ---- data parallel: one process per GPU, NCCL sum-allreduce of weight gradients ----- */
+#define CG_DP_ID_BYTES 128
+int cg_dp_unique_id(unsigned char id[CG_DP_ID_BYTES]);                      /* rank 0: ncclGetUniqueId */
+int cg_dp_init(int rank, int world, const unsigned char id[CG_DP_ID_BYTES]); /* every rank: ncclCommInitRank */
+int cg_dp_shutdown(void);
+int cg_set_device(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CG_GRAPH_H */

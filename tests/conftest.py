@@ -4,8 +4,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
 
 
 def pytest_configure(config):
@@ -24,8 +25,15 @@ def oracle():
     return o
 
 
-@pytest.fixture(scope="session")
+@pytest.fixture()
 def cg():
-    """The product API over libcg_b200.so (GPU tests only)."""
+    """The product API over libcg_b200.so (GPU tests only), reset to the reference-faithful defaults."""
     import computational_graph_b200 as pkg
-    return pkg.get_api()
+    api = pkg.get_api()
+    api.set_mode("exact")
+    api.set_tf32(False)
+    api.set_fix_act_grad(False)
+    api.set_fuse(True)
+    api.set_cuda_graph(True)
+    api.set_strict_gemm_max(64)
+    return api

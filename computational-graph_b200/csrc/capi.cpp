@@ -378,3 +378,43 @@ float reduce_sum(const Matrix* m) {
 }
 
 }  // extern "C"
+
+// Instrumented pass: one iteration launched eagerly with a CUDA event between every step, on the library
+// stream. kind_ms / kind_count are indexed by Step::Kind {EW, AVG, GEMM, ALLREDUCE}; max_gemm_* describe the
+// largest product (by flop) for the roofline line of bench.py.
+extern "C" int cg_profile_iteration(cg_function* f, float lr, double kind_ms[4], unsigned long long kind_count[4],
+                                    double* max_gemm_flop, double* max_gemm_ms_avg, unsigned long long* max_gemm_count) {
+  return guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    Plan& p = ensure_plan(*F(f), lr);
+    const size_t n = p.steps.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CG_CUDA(cudaEventCreate(&e));
+    const int saved = rt.use_graph;
+    CG_CUDA(cudaEventRecord(ev[0], rt.stream));
+    for (size_t i = 0; i < n; i++) {
+      plan_launch_step(p, i, rt.stream);
+      CG_CUDA(cudaEventRecord(ev[i + 1], rt.stream));
+    }
+    rt.use_graph = saved;
+    rt.launches += n;
+    CG_CUDA(cudaStreamSynchronize(rt.stream));
+    for (int k = 0; k < 4; k++) kind_ms[k] = 0.0, kind_count[k] = 0;
+    double best_flop = 0.0;
+    for (size_t i = 0; i < n; i++)
+      if (p.steps[i].kind == Step::GEMM) best_flop = std::max(best_flop, plan_step_flop(p, i));
+    double best_ms = 0.0;
+    unsigned long long best_cnt = 0;
+    for (size_t i = 0; i < n; i++) {
+      float ms = 0.0f;
+      CG_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      kind_ms[p.steps[i].kind] += ms;
+      kind_count[p.steps[i].kind]++;
+      if (p.steps[i].kind == Step::GEMM && plan_step_flop(p, i) == best_flop) best_ms += ms, best_cnt++;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    *max_gemm_flop = best_flop;
+    *max_gemm_ms_avg = best_cnt ? best_ms / (double)best_cnt : 0.0;
+    *max_gemm_count = best_cnt;
+  });
+}

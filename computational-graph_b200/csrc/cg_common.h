@@ -114,6 +114,7 @@ void launch_gemm_f32(const float* A, bool ta, const float* B, bool tb, float* C,
 // TF32 tensor-core path (tcgen05 + TMA + TMEM, gemm_tcgen05.cu). Returns false when the shape is not
 // eligible (caller falls back to launch_gemm_f32).
 bool gemm_tf32_eligible(int m, int n, int k, bool ta, bool tb);
+bool gemm_tf32_aligned(const float* A, const float* B, int lda, int ldb);
 void launch_gemm_tf32(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda,
                       int ldb, int ldc, const GemmEpilogue& epi, cudaStream_t stream);
 

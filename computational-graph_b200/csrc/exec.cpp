@@ -15,7 +15,7 @@ static void upload_inputs(Plan& p, const std::vector<Arg>& args) {
     const bool is_matrix = !(a->h == 0 && a->w == 0);
     if (is_matrix != f->value.is_matrix) throw Error("panic: Cannot copy mismatched Constants.");
     if (is_matrix && (a->h != f->value.h || a->w != f->value.w)) throw Error("ERROR: copy_matrix: dims differ");
-    value_upload_rowmajor(f->value, a->vals);
+    value_upload_rowmajor(f->value, a->vals, /*sync=*/false);  // minimize() synchronises before returning
   }
 }
 
@@ -62,7 +62,10 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
   }
 
   float* trace_dev = nullptr;
-  if (trace && iters > 0) CG_CUDA(cudaMalloc(&trace_dev, (size_t)iters * p.root_n * sizeof(float)));
+  const bool direct_trace = trace && iters == 1;  // one iteration: read the root value straight back
+  if (trace && iters > 1) CG_CUDA(cudaMalloc(&trace_dev, (size_t)iters * p.root_n * sizeof(float)));
+  if (direct_trace && p.root_is_leaf)
+    CG_CUDA(cudaMemcpyAsync(trace, p.root_ptr, p.root_n * sizeof(float), cudaMemcpyDeviceToHost, rt.stream));
   for (int i = 0; i < iters; i++) {
     // the traced value is the forward value of iteration i, i.e. before its update (Q12)
     if (trace_dev && p.root_is_leaf)
@@ -75,6 +78,11 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
       CG_CUDA(cudaMemcpyAsync(trace_dev + (size_t)i * p.root_n, p.root_ptr, p.root_n * sizeof(float),
                               cudaMemcpyDeviceToDevice, rt.stream));
     if (print_freq > 0 && (i + 1) % print_freq == 0) print_value(f.value);
+  }
+  if (direct_trace) {
+    if (!p.root_is_leaf)
+      CG_CUDA(cudaMemcpyAsync(trace, p.root_ptr, p.root_n * sizeof(float), cudaMemcpyDeviceToHost, rt.stream));
+    CG_CUDA(cudaStreamSynchronize(rt.stream));
   }
   if (trace_dev) {
     CG_CUDA(cudaMemcpyAsync(trace, trace_dev, (size_t)iters * p.root_n * sizeof(float), cudaMemcpyDeviceToHost,

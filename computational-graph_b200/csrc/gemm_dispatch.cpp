@@ -10,7 +10,7 @@ void launch_gemm(const float* A, bool ta, const float* B, bool tb, float* C, int
   const int mx = m > n ? (m > k ? m : k) : (n > k ? n : k);
   if (mx <= rt.strict_gemm_max) {
     launch_gemm_f32(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, /*strict=*/true, epi, stream);
-  } else if (allow_tf32 && gemm_tf32_eligible(m, n, k, ta, tb)) {
+  } else if (allow_tf32 && gemm_tf32_eligible(m, n, k, ta, tb) && gemm_tf32_aligned(A, B, lda, ldb)) {
     launch_gemm_tf32(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
   } else {
     launch_gemm_f32(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, /*strict=*/false, epi, stream);

@@ -76,25 +76,23 @@ Function* make_scalar_leaf(Kind kind, const char* name, float x) {
   return new_leaf(kind, name, std::move(v));
 }
 
-void value_upload_rowmajor(Value& v, const float* src) {
+void value_upload_rowmajor(Value& v, const float* src, bool sync) {
   // Matrix::new -> set_array(values, transpose = true) (matrix.rs:59-66, cpu/matrix.cpp:26-36)
   Runtime& rt = Runtime::get();
   const size_t n = v.size();
-  if (!v.is_matrix) {
-    CG_CUDA(cudaMemcpyAsync(v.buf->ptr, src, sizeof(float), cudaMemcpyHostToDevice, rt.stream));
-    CG_CUDA(cudaStreamSynchronize(rt.stream));
-    return;
-  }
-  if (v.h == 1 || v.w == 1) {  // a vector: both layouts coincide
+  if (!v.is_matrix || v.h == 1 || v.w == 1) {  // a scalar or a vector: both layouts coincide
     CG_CUDA(cudaMemcpyAsync(v.buf->ptr, src, n * sizeof(float), cudaMemcpyHostToDevice, rt.stream));
-    CG_CUDA(cudaStreamSynchronize(rt.stream));
-    return;
+  } else {
+    // stream-ordered: the staging buffer is reused by the next upload only after this transpose has run
+    if (!rt.staging || rt.staging->n < n) {
+      CG_CUDA(cudaStreamSynchronize(rt.stream));
+      rt.staging = DevBuf::alloc(n);
+    }
+    CG_CUDA(cudaMemcpyAsync(rt.staging->ptr, src, n * sizeof(float), cudaMemcpyHostToDevice, rt.stream));
+    launch_rowmajor_to_colmajor(rt.staging->ptr, v.buf->ptr, v.h, v.w, rt.stream);
+    rt.launches++;
   }
-  BufRef staging = DevBuf::alloc(n);
-  CG_CUDA(cudaMemcpyAsync(staging->ptr, src, n * sizeof(float), cudaMemcpyHostToDevice, rt.stream));
-  launch_rowmajor_to_colmajor(staging->ptr, v.buf->ptr, v.h, v.w, rt.stream);
-  rt.launches++;
-  CG_CUDA(cudaStreamSynchronize(rt.stream));
+  if (sync) CG_CUDA(cudaStreamSynchronize(rt.stream));  // the caller may free `src` as soon as we return
 }
 
 Function* make_matrix_leaf(Kind kind, const char* name, unsigned h, unsigned w, const float* vals) {

@@ -79,6 +79,7 @@ struct Runtime {
   unsigned long long launches = 0;  // kernels launched by this library (bench.py's gpu_launches)
   int* flag = nullptr;   // device int for all_equal / all_less_than
   float* red_ws = nullptr;
+  BufRef staging;        // grow-only device staging buffer for row-major uploads (never freed in a loop)
   static Runtime& get();
   void init();
 };
@@ -96,7 +97,7 @@ Function* make_dot(const Function& a, bool t1, const Function& b, bool t2);
 bool value_all_equal(const Value& v, float x);
 bool value_all_less_than(const Value& v, float x);
 void value_download(const Value& v, float* dst);  // storage (column-major) order, as get_array
-void value_upload_rowmajor(Value& v, const float* src_rowmajor);
+void value_upload_rowmajor(Value& v, const float* src_rowmajor, bool sync = true);
 
 struct Arg {
   std::string name;

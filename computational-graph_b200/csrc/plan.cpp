@@ -40,7 +40,9 @@ struct Builder {
   std::unordered_map<const Expr*, int> node_val;      // shared body -> forward value
   std::unordered_set<const Function*> seen_inputs, seen_params;
 
-  Builder(Plan& plan, float lr_, int fix) : p(plan), lr(lr_), fix_act_grad(fix) {}
+  bool dp = false;
+
+  Builder(Plan& plan, float lr_, int fix) : p(plan), lr(lr_), fix_act_grad(fix), dp(dp_enabled()) {}
 
   static Shape shape_of(const Function& f) { return Shape{f.value.is_matrix, f.value.h, f.value.w}; }
 
@@ -257,6 +259,17 @@ struct Builder {
         // the result (ops.rs:405), which coincides for its square-only products (Q7)
         to_f1 = equals_dot(shape_of(*e.f1), error, false, read(*e.f2), !e.t2);
         to_f2 = equals_dot(shape_of(*e.f2), read(*e.f1), !e.t1, error, false);
+        if (dp && e.f2->has_params) {
+          // Data parallel: the rows of every left operand are the sharded batch dimension, so the
+          // right-operand (weight) gradient X^T.E is a per-rank partial sum: sum-allreduce it, in place.
+          Instr ar;
+          ar.op = IOp::AllReduce;
+          ar.a = to_f2;
+          ar.dst = new_val(sh(to_f2));
+          p.vals[ar.dst].alias_of = to_f2;
+          p.tape.push_back(ar);
+          to_f2 = ar.dst;
+        }
         break;
       default: break;
     }
@@ -782,9 +795,21 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr) {
   return plan;
 }
 
+double plan_step_flop(const Plan& p, size_t i) {
+  const Step& s = p.steps[i];
+  if (s.kind != Step::GEMM) return 0.0;
+  const Shape &as = p.vals[s.ins.a].sh, &cs = p.vals[s.ins.dst].sh;
+  return 2.0 * cs.h * cs.w * (double)(s.ins.ta ? as.h : as.w);
+}
+
 void plan_launch_iteration(Plan& p, cudaStream_t stream) {
+  for (size_t i = 0; i < p.steps.size(); i++) plan_launch_step(p, i, stream);
+}
+
+void plan_launch_step(Plan& p, size_t index, cudaStream_t stream) {
   Runtime& rt = Runtime::get();
-  for (Step& s : p.steps) {
+  Step& s = p.steps[index];
+  {
     switch (s.kind) {
       case Step::EW: launch_ew_program(s.prog, stream); break;
       case Step::AVG: {

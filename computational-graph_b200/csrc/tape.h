@@ -95,5 +95,7 @@ struct Plan {
 
 std::shared_ptr<Plan> build_plan(Function& root, float lr);
 void plan_launch_iteration(Plan& p, cudaStream_t stream);  // enqueue the kernels of one iteration
+void plan_launch_step(Plan& p, size_t index, cudaStream_t stream);
+double plan_step_flop(const Plan& p, size_t index);
 
 }  // namespace cg

@@ -95,6 +95,11 @@ const char *cg_last_error(void);
 /* Times `reps` replays of f's iteration with CUDA events on the library stream; returns ms per iteration. */
 double cg_time_iterations(cg_function *f, float learn_rate, int warmup, int reps);
 
+/* One iteration launched eagerly with a CUDA event between every kernel: per-kind device time
+ * (index 0 elementwise, 1 reduce, 2 product, 3 all-reduce) and the average duration of the largest product. */
+int cg_profile_iteration(cg_function *f, float learn_rate, double kind_ms[4], unsigned long long kind_count[4],
+                         double *max_gemm_flop, double *max_gemm_ms_avg, unsigned long long *max_gemm_count);
+
 /* ---- data parallel: one process per GPU, NCCL sum-allreduce of weight gradients ----- */
 #define CG_DP_ID_BYTES 128
 int cg_dp_unique_id(unsigned char id[CG_DP_ID_BYTES]);                      /* rank 0: ncclGetUniqueId */

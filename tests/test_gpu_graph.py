@@ -183,3 +183,24 @@ def test_errors_surface_as_reference_messages(cg):
     x = F.input("x", [2, 2])
     with pytest.raises(GraphError, match="missing arg"):
         (x + F.param("p", cg.Constant(np.ones((2, 2), np.float32)))).minimize({}, 0.1, 1)
+
+
+def test_lstm_tf32_tensor_core_path(cg, oracle):
+    """LSTM in dag mode with every product on the tcgen05 TF32 kernel (forward NN, dX NT, dW TN with the fused
+    SGD epilogue, dX accumulation epilogue). TF32 keeps 10 mantissa bits: tolerance 1e-3 (north_star)."""
+    cg.set_mode("dag")
+    cg.set_tf32(True)
+    oracle.set_mode("dag")
+    try:
+        fg = readme_lstm(cg, 256, T=2, seed=21, batch=256, d_in=256, scale=1.0 / 16)
+        fo = readme_lstm(oracle, 256, T=2, seed=21, batch=256, d_in=256, scale=1.0 / 16)
+        st = cg.plan_stats(fg, 0.01)
+        assert st["gemms"] > 0 and st["gemms_fused_sgd"] > 0
+        tg = fg.minimize({}, 0.01, 2, trace=True)
+        to = fo.minimize({}, 0.01, 2, trace=True)
+        assert rel_err(tg, to) < 1e-3
+        lg, lo = leaves_dict(fg), leaves_dict(fo)
+        for k in lg:
+            assert rel_err(lg[k], lo[k]) < 1e-3, k
+    finally:
+        oracle.set_mode("exact")

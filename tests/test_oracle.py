@@ -1,0 +1,214 @@
+"""The CPU oracle pinned against everything the reference offers for this path (no GPU needed):
+  * the reference's own 15 threshold tests (src/main.rs:85-166),
+  * the C1 golden trajectory derivable with pure IEEE arithmetic,
+  * the restated arithmetic ("port") against the REFERENCE-COMPILED CPU backend (oracle/_ref), symbol by symbol,
+  * the committed golden vectors (tests/golden, generated through the reference-compiled backend),
+  * the structural facts of the reference's tree walk (gemm counts per iteration, Q1/Q2/Q3/Q4 quirks).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import c2_graph, leaves_dict, readme_lstm, rel_err
+from matrix_abi import BINS, MAPS, Matrix, OracleMatrixAbi
+from reference_cases import CASES, run_case
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.int32)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_reference_thresholds(oracle, name):
+    res, goal = run_case(oracle, name, trace=True)
+    for f, _ in res:
+        assert f.all_less_than(goal), name
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_reference_suite_golden(oracle, name):
+    gold = np.load(os.path.join(GOLD, "reference_suite.npz"))
+    res, _ = run_case(oracle, name, trace=True)
+    for i, (f, tr) in enumerate(res):
+        assert np.array_equal(bits(tr), bits(gold[f"{name}/{i}/trace"]))
+        assert np.array_equal(bits(f.value()), bits(gold[f"{name}/{i}/final"]))
+
+
+@pytest.mark.parametrize("backend", ["ref", "port"])
+def test_port_equals_reference_compiled_backend_on_suite(oracle, backend):
+    """The restated arithmetic gives the same bits as the reference's own compiled CPU backend."""
+    gold = np.load(os.path.join(GOLD, "reference_suite.npz"))
+    if backend == "port":
+        oracle.use_port()
+    try:
+        for name in CASES:
+            res, _ = run_case(oracle, name, trace=True)
+            for i, (f, tr) in enumerate(res):
+                assert np.array_equal(bits(tr), bits(gold[f"{name}/{i}/trace"])), (backend, name)
+    finally:
+        if not oracle.use_ref("O0"):
+            oracle.use_port()
+
+
+def test_c1_golden(oracle):
+    F = oracle.Function
+    x = F.scalar_param("x", 1.0)
+    f = (x + F.scalar(3.0)).sq()
+    tr = f.minimize({}, 0.01, 1000, trace=True)
+    golden = {0: 16.0, 1: 15.366400718688965, 2: 14.757889747619629, 9: 11.122164726257324,
+              99: 0.2930106520652771, 999: 3.2741809263825417e-11}
+    for i, v in golden.items():
+        assert np.float32(tr[i]) == np.float32(v)
+    assert f.leaves()[0][1] == np.float32(-2.9999942779541016)
+    g = np.load(os.path.join(GOLD, "c1_scalar.npz"))
+    assert np.array_equal(bits(tr), bits(g["trace"]))
+
+
+def test_tanh_trajectory_of_survey(oracle):
+    """tanh_test's 10-step forward trajectory through the reference-compiled map_tanh etc."""
+    want = [0.4621172, -0.278862, -0.8362842, -0.906817, -0.9337634, -0.9483457, -0.9575633, -0.9639423, -0.9686293,
+            -0.9722237]
+    res, _ = run_case(oracle, "tanh_test", trace=True)
+    for f, tr in res:
+        assert np.allclose(np.asarray(tr).reshape(10, -1)[:, 0], want, rtol=0, atol=5e-7)
+
+
+@pytest.mark.parametrize("name,builder", [("c2_elementwise_32", lambda o: (c2_graph(o, 32), 20, "exact")),
+                                          ("c3_lstm_d5", lambda o: (readme_lstm(o, 5), 10, "exact")),
+                                          ("c3_lstm_d10", lambda o: (readme_lstm(o, 10), 10, "exact")),
+                                          ("lstm_dag_d6_T3", lambda o: (readme_lstm(o, 6, T=3, seed=77), 10, "dag"))])
+def test_graph_goldens(oracle, name, builder):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    mode = builder(oracle)[2]
+    oracle.set_mode(mode)
+    try:
+        f, iters, _ = builder(oracle)
+        tr = f.minimize({}, 0.01, iters, trace=True)
+        assert np.array_equal(bits(tr), bits(g["trace"]))
+        for k, v in leaves_dict(f).items():
+            assert np.array_equal(bits(v), bits(g[k.replace(":", "_")])), k
+    finally:
+        oracle.set_mode("exact")
+
+
+def _have_ref(oracle):
+    ok = oracle.use_ref("O0")
+    return ok
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 2), (5, 3), (17, 33), (64, 64)])
+def test_port_symbols_equal_reference_symbols(oracle, shape):
+    """Every one of the matrix symbols: restated port == reference-compiled .so, bit for bit (incl. libm calls,
+    which resolve to the same glibc). The square gemm is the reference's own (valid only for square, Q7)."""
+    if not _have_ref(oracle):
+        pytest.skip("oracle/_ref not built (no /root/reference and no prebuilt copy)")
+    rng = np.random.default_rng(shape[0] * 131 + shape[1])
+    a = rng.uniform(-3, 3, shape).astype(np.float32)
+    b = rng.uniform(-3, 3, shape).astype(np.float32)
+    a.reshape(-1)[0] = -0.0
+    results = {}
+    for backend in ("ref", "port"):
+        if backend == "port":
+            oracle.use_port()
+        else:
+            oracle.use_ref("O0")
+        o = OracleMatrixAbi(oracle)
+        ma, mb, r = o.new(*shape, a), o.new(*shape, b), o.new(*shape)
+        out = []
+        for k in range(len(MAPS)):
+            o.lib.orc_sym_map(k, C.byref(ma), C.byref(r))
+            out.append(o.get(r))
+        for k in range(len(BINS)):
+            o.lib.orc_sym_elemwise(k, C.byref(ma), C.byref(mb), C.byref(r))
+            out.append(o.get(r))
+            o.lib.orc_sym_broadcast(k, C.byref(ma), 1.25, C.byref(r))
+            out.append(o.get(r))
+            o.lib.orc_sym_broadcast_rev(k, 1.25, C.byref(ma), C.byref(r))
+            out.append(o.get(r))
+        out.append(np.float32(o.lib.orc_sym_reduce_sum(C.byref(ma))))
+        out.append(np.float32(o.lib.orc_sym_all_less_than(C.byref(ma), 3.5)))
+        out.append(np.float32(o.lib.orc_sym_all_equal(C.byref(ma), float(a[0, 0]))))
+        if shape[0] == shape[1]:
+            for t1 in (False, True):
+                for t2 in (False, True):
+                    o.lib.orc_sym_gemm(C.byref(ma), t1, C.byref(mb), t2, C.byref(r))
+                    out.append(o.get(r))
+        results[backend] = out
+    oracle.use_ref("O0")
+    assert len(results["ref"]) == len(results["port"])
+    for x, y in zip(results["ref"], results["port"]):
+        assert np.array_equal(bits(x), bits(y))
+
+
+def test_o0_and_o3_reference_builds_agree(oracle):
+    """the -O0 build (the reference's build.rs flags) and -O3 -ffp-contract=off give the same bits."""
+    if not oracle.use_ref("O3"):
+        pytest.skip("oracle/_ref not built")
+    try:
+        f = readme_lstm(oracle, 5)
+        t3 = f.minimize({}, 0.01, 5, trace=True)
+    finally:
+        oracle.use_ref("O0")
+    f = readme_lstm(oracle, 5)
+    t0 = f.minimize({}, 0.01, 5, trace=True)
+    assert np.array_equal(bits(t0), bits(t3))
+
+
+def test_tree_walk_gemm_counts(oracle):
+    """Q2: the un-memoised walk does 39 forward + 78 backward gemms per iteration at T=2
+    (15 unique products), 216 + 432 at T=3; growth ~5.4x per step."""
+    for T, fwd in ((1, 6), (2, 39), (3, 216)):
+        f = readme_lstm(oracle, 5, T=T)
+        size, dots = oracle.tree_size(f)
+        assert dots == fwd
+        oracle.reset_counts()
+        f.minimize({}, 0.01, 1)
+        assert oracle.gemm_count() == 3 * fwd
+    f = readme_lstm(oracle, 5, T=2)
+    assert len(f.leaves()) == 28
+
+
+def test_quirks(oracle):
+    F = oracle.Function
+    # Q4: sigmoid(x) with x == 0.5 is eliminated at construction; 0 - x is x
+    x = F.scalar_param("x", 0.5)
+    assert oracle.lib.orc_kind(x.sigmoid()._h) == oracle.lib.orc_kind(x._h)
+    z = F.scalar(0.0)
+    assert oracle.lib.orc_kind((z - x)._h) == oracle.lib.orc_kind(x._h)
+    # Q1: the two uses of x in (x - 2) * (x + b) diverge
+    f = ((x - F.scalar(2.)) * (x + F.matrix(2, 2, [1.2, -1., 0., 1.5]))).sq()
+    f.minimize({}, 0.04, 3)
+    (n0, v0), (n1, v1) = f.leaves()
+    assert n0 == n1 == "x" and v0 != v1
+    # Q3: sigmoid hands its child the local derivative: d/dw of 10 * sigmoid(w) moves w by lr * s'(w), not 10x that
+    # (w starts at 2: a node's stale construction-time value equals its child's, and 1 is Mul's identity — Q4)
+    w = F.scalar_param("w", 2.0)
+    g = F.scalar(10.0) * w.sigmoid()
+    g.minimize({}, 1.0, 1)
+    s = 1.0 / (1.0 + np.exp(-2.0))
+    assert abs(float(g.leaves()[0][1]) - (2.0 - s * (1 - s))) < 1e-6
+    # ... and the stale-value elimination itself: sigmoid(w) with w == 1 carries the value 1 => 10 * it is just 10
+    w1 = F.scalar_param("w", 1.0)
+    assert (F.scalar(10.0) * w1.sigmoid()).leaves() == []
+    # Q5: scalar <- matrix gradient is averaged: x + ones(2,2)*c with root error ones => x -= lr * avg(1) = lr
+    xs = F.scalar_param("x", 0.5)
+    h = xs + F.matrix(2, 2, [1., 2., 3., 4.])
+    h.minimize({}, 0.1, 1)
+    assert np.float32(h.leaves()[0][1]) == np.float32(0.5) - np.float32(0.1)
+
+
+def test_dag_equals_exact_without_shared_nodes(oracle):
+    out = []
+    for mode in ("exact", "dag"):
+        oracle.set_mode(mode)
+        f = readme_lstm(oracle, 7, T=1, seed=3)
+        tr = f.minimize({}, 0.01, 5, trace=True)
+        out.append((tr, leaves_dict(f)))
+    oracle.set_mode("exact")
+    assert np.array_equal(bits(out[0][0]), bits(out[1][0]))
+    for k in out[0][1]:
+        assert np.array_equal(bits(out[0][1][k]), bits(out[1][1][k]))

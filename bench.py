@@ -209,12 +209,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(api.dp_unique_id()), dtype=torch.uint8).clone()
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        api.dp_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        pkg.dp.init_from_torch_distributed(api, local_rank)
     api.set_mode("dag")
     api.set_tf32(args.product == "tf32")
 

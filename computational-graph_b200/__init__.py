@@ -13,3 +13,4 @@ The directory name carries a hyphen (it is the reference's name); import it as
 from .api import Api, Constant, Function, GraphError  # noqa: F401
 from ._lib import load_library, library_path, get_api  # noqa: F401
 from . import lstm  # noqa: F401
+from . import dp  # noqa: F401

@@ -45,7 +45,8 @@ class ProductApi(Api):
 
     def __init__(self, lib: C.CDLL):
         super().__init__(lib, "cg_")
-        for name in ("set_tf32", "set_fix_act_grad", "set_fuse", "set_cuda_graph", "set_strict_gemm_max"):
+        for name in ("set_tf32", "set_fix_act_grad", "set_fuse", "set_cuda_graph", "set_strict_gemm_max",
+                     "set_graph_streams"):
             fn = self._sym(name)
             fn.restype, fn.argtypes = None, [C.c_int]
         lib.cg_launch_count.restype = C.c_ulonglong
@@ -70,6 +71,7 @@ class ProductApi(Api):
     def set_fuse(self, on: bool): self.lib.cg_set_fuse(int(on))
     def set_cuda_graph(self, on: bool): self.lib.cg_set_cuda_graph(int(on))
     def set_strict_gemm_max(self, dim: int): self.lib.cg_set_strict_gemm_max(int(dim))
+    def set_graph_streams(self, n: int): self.lib.cg_set_graph_streams(int(n))
     def set_device(self, dev: int): self._check(self.lib.cg_set_device(int(dev)))
     def launch_count(self) -> int: return int(self.lib.cg_launch_count())
     def synchronize(self): self._check(self.lib.cg_synchronize())

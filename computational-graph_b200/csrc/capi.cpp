@@ -158,6 +158,13 @@ void cg_set_fix_act_grad(int v) { guard_rc([&] { Runtime::get().fix_act_grad = v
 void cg_set_fuse(int v) { guard_rc([&] { Runtime::get().fuse = v; }); }
 void cg_set_cuda_graph(int v) { guard_rc([&] { Runtime::get().use_graph = v; }); }
 void cg_set_strict_gemm_max(int v) { guard_rc([&] { Runtime::get().strict_gemm_max = v; }); }
+void cg_set_graph_streams(int v) {
+  guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    if (rt.graph_streams != v) rt.dp_epoch++;  // captured graphs depend on it: invalidate cached plans
+    rt.graph_streams = v;
+  });
+}
 
 // ---- introspection ---------------------------------------------------------------------------------------------------
 static Plan& ensure_plan(Function& f, float lr) {
@@ -416,5 +423,61 @@ extern "C" int cg_profile_iteration(cg_function* f, float lr, double kind_ms[4],
     *max_gemm_flop = best_flop;
     *max_gemm_ms_avg = best_cnt ? best_ms / (double)best_cnt : 0.0;
     *max_gemm_count = best_cnt;
+  });
+}
+
+// Bring-up probe: a tcgen05 product on one stream and an elementwise program on another, timed alone and
+// together (ms). Answers whether the two kernels become co-resident on an SM.
+extern "C" int cg_debug_overlap(double out_ms[3]) {
+  return guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    const int B = 1024, H = 4096;
+    BufRef a = DevBuf::alloc((size_t)B * H), w = DevBuf::alloc((size_t)H * H), c = DevBuf::alloc((size_t)B * H);
+    BufRef e0 = DevBuf::alloc((size_t)H * H), e1 = DevBuf::alloc((size_t)H * H);
+    CG_CUDA(cudaMemset(a->ptr, 0, (size_t)B * H * 4));
+    CG_CUDA(cudaMemset(w->ptr, 0, (size_t)H * H * 4));
+    CG_CUDA(cudaMemset(e0->ptr, 0, (size_t)H * H * 4));
+    EwProgram p{};
+    p.n = (size_t)H * H;
+    p.n_in = 1, p.n_out = 1;
+    p.in[0] = e0->ptr, p.out[0] = e1->ptr;
+    int k = 0;
+    p.code[k++] = ew_encode(OP_LDR, 0);
+    p.code[k++] = ew_encode(OP_SIGMOID);
+    p.code[k++] = ew_encode(OP_TANH);
+    p.code[k++] = ew_encode(OP_SIGMOID);
+    p.code[k++] = ew_encode(OP_STG, 0);
+    p.n_ins = k;
+    cudaStream_t s1, s2;
+    CG_CUDA(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+    CG_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    cudaEvent_t ev[4];
+    for (auto& e : ev) CG_CUDA(cudaEventCreate(&e));
+    auto gem = [&](cudaStream_t s) {
+      for (int r = 0; r < 8; r++)
+        launch_gemm(a->ptr, false, w->ptr, false, c->ptr, B, H, H, B, H, B, GemmEpilogue{}, true, s);
+    };
+    auto eww = [&](cudaStream_t s) {
+      for (int r = 0; r < 2; r++) launch_ew_program(p, s);
+    };
+    for (int mode = 0; mode < 3; mode++) {
+      for (int rep = 0; rep < 2; rep++) {  // second repetition is the timed one
+        CG_CUDA(cudaDeviceSynchronize());
+        CG_CUDA(cudaEventRecord(ev[0], s1));
+        CG_CUDA(cudaStreamWaitEvent(s2, ev[0], 0));
+        if (mode == 0 || mode == 2) gem(s1);
+        if (mode == 1 || mode == 2) eww(s2);
+        CG_CUDA(cudaEventRecord(ev[1], s2));
+        CG_CUDA(cudaStreamWaitEvent(s1, ev[1], 0));
+        CG_CUDA(cudaEventRecord(ev[2], s1));
+        CG_CUDA(cudaEventSynchronize(ev[2]));
+        float ms = 0;
+        CG_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[2]));
+        out_ms[mode] = ms;
+      }
+    }
+    (void)rt;
+    cudaStreamDestroy(s1);
+    cudaStreamDestroy(s2);
   });
 }

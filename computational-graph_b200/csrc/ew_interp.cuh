@@ -83,81 +83,96 @@ __device__ __forceinline__ void ew_run(const Prog& p, size_t base, size_t stride
 #pragma unroll
   for (int j = 0; j < VEC; j++) acc[j] = 0.0f;
 
+  // Two-level dispatch, both levels dense => ptxas emits jump tables (BRX), not compare trees.
   const uint32_t n_ins = p.n_ins;
   for (uint32_t pc = 0; pc < n_ins; pc++) {
     const uint32_t ins = p.code[pc];
-    switch (ins) {
-#define CG_CASE_REG(K)                                                                   \
-  case (OP_LDR << 4) | K:                                                                \
-    _Pragma("unroll") for (int j = 0; j < VEC; j++) acc[j] = r[K][j];                    \
-    break;                                                                               \
-  case (OP_STR << 4) | K:                                                                \
-    _Pragma("unroll") for (int j = 0; j < VEC; j++) r[K][j] = acc[j];                    \
-    break;                                                                               \
-  case (OP_ADD << 4) | K:                                                                \
-    _Pragma("unroll") for (int j = 0; j < VEC; j++) acc[j] = __fadd_rn(acc[j], r[K][j]); \
-    break;                                                                               \
-  case (OP_SUB << 4) | K:                                                                \
-    _Pragma("unroll") for (int j = 0; j < VEC; j++) acc[j] = __fsub_rn(acc[j], r[K][j]); \
-    break;                                                                               \
-  case (OP_RSUB << 4) | K:                                                               \
-    _Pragma("unroll") for (int j = 0; j < VEC; j++) acc[j] = __fsub_rn(r[K][j], acc[j]); \
-    break;                                                                               \
-  case (OP_MUL << 4) | K:                                                                \
-    _Pragma("unroll") for (int j = 0; j < VEC; j++) acc[j] = __fmul_rn(acc[j], r[K][j]); \
-    break;
-      CG_FOR_EACH_REG(CG_CASE_REG)
-#undef CG_CASE_REG
-      case (OP_NEG << 4):
+    const uint32_t k = ins & 15u;
+    switch (ins >> 4) {
+#define CG_REG_SWITCH(STMT)                                         \
+  switch (k) {                                                      \
+    case 0: { constexpr int K = 0; STMT } break;                    \
+    case 1: { constexpr int K = 1; STMT } break;                    \
+    case 2: { constexpr int K = 2; STMT } break;                    \
+    case 3: { constexpr int K = 3; STMT } break;                    \
+    case 4: { constexpr int K = 4; STMT } break;                    \
+    case 5: { constexpr int K = 5; STMT } break;                    \
+    case 6: { constexpr int K = 6; STMT } break;                    \
+    case 7: { constexpr int K = 7; STMT } break;                    \
+    case 8: { constexpr int K = 8; STMT } break;                    \
+    case 9: { constexpr int K = 9; STMT } break;                    \
+    case 10: { constexpr int K = 10; STMT } break;                  \
+    default: { constexpr int K = 11; STMT } break;                  \
+  }
+      case OP_LDR:
+        CG_REG_SWITCH(_Pragma("unroll") for (int j = 0; j < VEC; j++) acc[j] = r[K][j];)
+        break;
+      case OP_STR:
+        CG_REG_SWITCH(_Pragma("unroll") for (int j = 0; j < VEC; j++) r[K][j] = acc[j];)
+        break;
+      case OP_ADD:
+        CG_REG_SWITCH(_Pragma("unroll") for (int j = 0; j < VEC; j++) acc[j] = __fadd_rn(acc[j], r[K][j]);)
+        break;
+      case OP_SUB:
+        CG_REG_SWITCH(_Pragma("unroll") for (int j = 0; j < VEC; j++) acc[j] = __fsub_rn(acc[j], r[K][j]);)
+        break;
+      case OP_RSUB:
+        CG_REG_SWITCH(_Pragma("unroll") for (int j = 0; j < VEC; j++) acc[j] = __fsub_rn(r[K][j], acc[j]);)
+        break;
+      case OP_MUL:
+        CG_REG_SWITCH(_Pragma("unroll") for (int j = 0; j < VEC; j++) acc[j] = __fmul_rn(acc[j], r[K][j]);)
+        break;
+#undef CG_REG_SWITCH
+      case OP_LDI: {
+        const float s = p.imm[k];
+#pragma unroll
+        for (int j = 0; j < VEC; j++) acc[j] = s;
+      } break;
+      case OP_MULI: {
+        const float s = p.imm[k];
+#pragma unroll
+        for (int j = 0; j < VEC; j++) acc[j] = __fmul_rn(acc[j], s);
+      } break;
+      case OP_NEG:
 #pragma unroll
         for (int j = 0; j < VEC; j++) acc[j] = -acc[j];
         break;
-      case (OP_SQ << 4):
+      case OP_SQ:
 #pragma unroll
         for (int j = 0; j < VEC; j++) acc[j] = __fmul_rn(acc[j], acc[j]);
         break;
-      case (OP_ABS_M << 4):
+      case OP_ABS_M:
 #pragma unroll
         for (int j = 0; j < VEC; j++) acc[j] = acc[j] < 0.0f ? -acc[j] : acc[j];
         break;
-      case (OP_SGN_M << 4):
+      case OP_SGN_M:
 #pragma unroll
         for (int j = 0; j < VEC; j++) acc[j] = acc[j] < 0.0f ? -1.0f : 1.0f;
         break;
-      case (OP_ABS_S << 4):
+      case OP_ABS_S:
 #pragma unroll
         for (int j = 0; j < VEC; j++) acc[j] = fabsf(acc[j]);
         break;
-      case (OP_SGN_S << 4):
+      case OP_SGN_S:
 #pragma unroll
         for (int j = 0; j < VEC; j++) acc[j] = ew_sgn_scalar(acc[j]);
         break;
-      case (OP_SIGMOID << 4):
+      case OP_SIGMOID:
 #pragma unroll
         for (int j = 0; j < VEC; j++) acc[j] = ew_sigmoid(acc[j]);
         break;
-      case (OP_TANH << 4):
+      case OP_TANH:
 #pragma unroll
         for (int j = 0; j < VEC; j++) acc[j] = tanhf(acc[j]);
         break;
-      case (OP_ONE_MINUS << 4):
+      case OP_ONE_MINUS:
 #pragma unroll
         for (int j = 0; j < VEC; j++) acc[j] = __fsub_rn(1.0f, acc[j]);
         break;
-      default: {
-        const uint32_t op = ins >> 4, k = ins & 15u;
-        if (op == OP_STG) {
-          ew_store<VEC>(p.out[k], base, stride, n, acc);
-        } else if (op == OP_LDI) {
-          const float s = p.imm[k];
-#pragma unroll
-          for (int j = 0; j < VEC; j++) acc[j] = s;
-        } else if (op == OP_MULI) {
-          const float s = p.imm[k];
-#pragma unroll
-          for (int j = 0; j < VEC; j++) acc[j] = __fmul_rn(acc[j], s);
-        }
-      } break;
+      case OP_STG:
+        ew_store<VEC>(p.out[k], base, stride, n, acc);
+        break;
+      default: break;
     }
   }
 }

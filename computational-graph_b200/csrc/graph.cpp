@@ -37,6 +37,7 @@ void Runtime::init() {
   if (const char* s = getenv("CG_FIX_ACT_GRAD")) fix_act_grad = atoi(s);
   if (const char* s = getenv("CG_FUSE")) fuse = atoi(s);
   if (const char* s = getenv("CG_CUDA_GRAPH")) use_graph = atoi(s);
+  if (const char* s = getenv("CG_GRAPH_STREAMS")) graph_streams = atoi(s);
 }
 
 static void fill_device(float* ptr, size_t n, float v) {

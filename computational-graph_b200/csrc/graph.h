@@ -74,6 +74,8 @@ struct Runtime {
   int fix_act_grad = 0;  // 0 = reproduce Q3
   int fuse = 1;          // 0 = one kernel per IR instruction (debug / ablation)
   int use_graph = 1;     // capture each iteration as a CUDA graph
+  int graph_streams = 4; // side streams used when an iteration is captured as a DAG (0 = single stream)
+  std::vector<cudaStream_t> side_streams;
   int dp_epoch = 0;      // bumped whenever the data-parallel configuration changes (invalidates plans)
   int strict_gemm_max = 64;  // products with max(m,n,k) <= this use the bit-exact strict kernel
   unsigned long long launches = 0;  // kernels launched by this library (bench.py's gpu_launches)

@@ -10,8 +10,8 @@ namespace cg {
 // ------------------------------------------------------------------------------------------------
 constexpr int EW_THREADS = 256;
 
-template <int VEC>
-__global__ void __launch_bounds__(EW_THREADS) ew_program_kernel(const __grid_constant__ EwProgram p) {
+template <int VEC, int MIN_BLOCKS>
+__global__ void __launch_bounds__(EW_THREADS, MIN_BLOCKS) ew_program_kernel(const __grid_constant__ EwProgram p) {
   const size_t tile_elems = (size_t)EW_THREADS * VEC;
   const size_t stride = (size_t)EW_THREADS * 4;
   for (size_t tile = blockIdx.x; tile * tile_elems < p.n; tile += gridDim.x) {
@@ -20,16 +20,38 @@ __global__ void __launch_bounds__(EW_THREADS) ew_program_kernel(const __grid_con
   }
 }
 
+static int ew_vec_choice() {
+  static int v = [] {
+    const char* e = getenv("CG_EW_VEC");
+    return e ? atoi(e) : 4;
+  }();
+  return v;
+}
+
 void launch_ew_program(const EwProgram& p, cudaStream_t stream) {
   if (p.n == 0) return;
-  // Small domains: VEC = 4 keeps more threads busy; large domains: VEC = 8 amortises the dispatch.
-  if (p.n <= (size_t)EW_THREADS * 4 * kNumSMs) {
-    size_t tiles = (p.n + EW_THREADS * 4 - 1) / (EW_THREADS * 4);
-    ew_program_kernel<4><<<(unsigned)tiles, EW_THREADS, 0, stream>>>(p);
-  } else {
+  static bool configured = false;
+  if (!configured) {
+    // Same shared-memory carveout as the product kernel (which owns ~200 KB of the SM): a CTA of this kernel can
+    // then be co-resident with a product CTA when the iteration graph runs them on parallel branches.
+    int carve = cudaSharedmemCarveoutMaxShared;
+    if (const char* e = getenv("CG_EW_CARVEOUT")) carve = atoi(e);
+    if (carve >= -1) {
+      cudaFuncSetAttribute(ew_program_kernel<4, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      cudaFuncSetAttribute(ew_program_kernel<8, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
+    configured = true;
+  }
+  // VEC = 4 (one float4 per operand per thread, <= 128 registers, two CTAs per SM — or one next to a product
+  // CTA when the graph runs them concurrently); VEC = 8 halves the dispatch overhead per element but owns the SM.
+  if (ew_vec_choice() == 8 && p.n > (size_t)EW_THREADS * 4 * kNumSMs) {
     size_t tiles = (p.n + EW_THREADS * 8 - 1) / (EW_THREADS * 8);
     size_t grid = tiles < (size_t)kNumSMs * 16 ? tiles : (size_t)kNumSMs * 16;
-    ew_program_kernel<8><<<(unsigned)grid, EW_THREADS, 0, stream>>>(p);
+    ew_program_kernel<8, 1><<<(unsigned)grid, EW_THREADS, 0, stream>>>(p);
+  } else {
+    size_t tiles = (p.n + EW_THREADS * 4 - 1) / (EW_THREADS * 4);
+    size_t grid = tiles < (size_t)kNumSMs * 16 ? tiles : (size_t)kNumSMs * 16;
+    ew_program_kernel<4, 2><<<(unsigned)grid, EW_THREADS, 0, stream>>>(p);
   }
   CG_CUDA(cudaGetLastError());
 }

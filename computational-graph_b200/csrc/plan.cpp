@@ -20,6 +20,7 @@ namespace cg {
 Plan::~Plan() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (graph) cudaGraphDestroy(graph);
+  for (cudaEvent_t e : events) cudaEventDestroy(e);
 }
 
 namespace {

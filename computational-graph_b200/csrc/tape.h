@@ -90,6 +90,7 @@ struct Plan {
   std::vector<Function*> param_leaves;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
+  std::vector<cudaEvent_t> events;  // one per step (+1 fork event) for the multi-stream capture
   ~Plan();
 };
 

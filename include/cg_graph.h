@@ -82,6 +82,7 @@ void cg_set_fix_act_grad(int on);     /* 1: sigmoid/tanh pass error*derivative (
 void cg_set_fuse(int on);             /* 0: one kernel per tape instruction (ablation) */
 void cg_set_cuda_graph(int on);       /* 0: launch kernels eagerly instead of replaying a CUDA graph */
 void cg_set_strict_gemm_max(int dim); /* products with max(m,n,k) <= dim use the bit-exact kernel */
+void cg_set_graph_streams(int n);     /* side streams of the per-iteration CUDA graph (0: one linear stream) */
 
 /* ---- introspection -------------------------------------------------------------------------------- */
 typedef struct {

@@ -3,7 +3,10 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Optional
+import weakref
+from typing import Dict, List, Optional
+
+import numpy as np
 
 from .api import Api
 
@@ -34,7 +37,7 @@ class PlanStats(C.Structure):
     """`cg_plan_stats` (include/cg_graph.h)."""
     _fields_ = [(n, C.c_ulonglong) for n in ("tape_instrs", "live_instrs", "kernels_per_iter", "ew_kernels", "gemms",
                                              "gemms_fused_sgd", "reduces", "arena_bytes")] + \
-               [("gemm_flop_per_iter", C.c_double), ("ew_bytes_per_iter", C.c_double)]
+               [("gemm_flop_per_iter", C.c_double), ("ew_bytes_per_iter", C.c_double), ("ew_specialised", C.c_ulonglong)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -46,7 +49,7 @@ class ProductApi(Api):
     def __init__(self, lib: C.CDLL):
         super().__init__(lib, "cg_")
         for name in ("set_tf32", "set_fix_act_grad", "set_fuse", "set_cuda_graph", "set_strict_gemm_max",
-                     "set_graph_streams"):
+                     "set_graph_streams", "set_io_graph"):
             fn = self._sym(name)
             fn.restype, fn.argtypes = None, [C.c_int]
         lib.cg_launch_count.restype = C.c_ulonglong
@@ -60,6 +63,41 @@ class ProductApi(Api):
         lib.cg_dp_unique_id.restype, lib.cg_dp_unique_id.argtypes = C.c_int, [C.c_char_p]
         lib.cg_dp_init.restype, lib.cg_dp_init.argtypes = C.c_int, [C.c_int, C.c_int, C.c_char_p]
         lib.cg_dp_shutdown.restype = C.c_int
+        lib.cg_set_ew_jit_min.restype, lib.cg_set_ew_jit_min.argtypes = None, [C.c_longlong]
+        lib.cg_ew_jit_selftest.restype = C.c_longlong
+        lib.cg_host_alloc.restype, lib.cg_host_alloc.argtypes = C.c_void_p, [C.c_size_t]
+        lib.cg_host_free.restype, lib.cg_host_free.argtypes = None, [C.c_void_p]
+        self._pinned_free: Dict[int, List[int]] = {}  # nbytes -> page-locked blocks ready for reuse
+
+    # page-locked host buffers ---------------------------------------------------------------------
+    _PINNED_KEEP = 4  # blocks kept per size (page-locking is slow: ~ms per 16 MB)
+
+    def pinned_empty(self, shape) -> np.ndarray:
+        """float32 array in page-locked host memory (cg_host_alloc). Its block returns to a small reuse pool
+        when the array (and every view of it) has been garbage-collected."""
+        n = int(np.prod(shape))
+        nbytes = max(n, 1) * 4
+        free = self._pinned_free.setdefault(nbytes, [])
+        ptr = free.pop() if free else self.lib.cg_host_alloc(nbytes)
+        if not ptr:
+            self._check(-1)
+        arr = np.ctypeslib.as_array((C.c_float * max(n, 1)).from_address(ptr))[:n].reshape(shape)
+        base = arr
+        while isinstance(base.base, np.ndarray):
+            base = base.base
+        weakref.finalize(base, self._pinned_release, ptr, nbytes)
+        return arr
+
+    def _pinned_release(self, ptr: int, nbytes: int):
+        free = self._pinned_free.setdefault(nbytes, [])
+        if len(free) < self._PINNED_KEEP:
+            free.append(ptr)
+        else:
+            self.lib.cg_host_free(ptr)
+
+    def _trace_buffer(self, iters: int, size: int) -> np.ndarray:
+        # page-locked, so a 1-iteration call can read the root value back from inside the iteration graph
+        return self.pinned_empty((iters, size))
 
     def _check(self, rc: int):
         if rc != 0:
@@ -72,6 +110,8 @@ class ProductApi(Api):
     def set_cuda_graph(self, on: bool): self.lib.cg_set_cuda_graph(int(on))
     def set_strict_gemm_max(self, dim: int): self.lib.cg_set_strict_gemm_max(int(dim))
     def set_graph_streams(self, n: int): self.lib.cg_set_graph_streams(int(n))
+    def set_ew_jit_min(self, min_elems: int): self.lib.cg_set_ew_jit_min(int(min_elems))
+    def set_io_graph(self, on: bool): self.lib.cg_set_io_graph(int(on))
     def set_device(self, dev: int): self._check(self.lib.cg_set_device(int(dev)))
     def launch_count(self) -> int: return int(self.lib.cg_launch_count())
     def synchronize(self): self._check(self.lib.cg_synchronize())

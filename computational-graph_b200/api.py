@@ -91,6 +91,10 @@ class GraphError(RuntimeError):
 class Api:
     """One bound graph library (product `cg_*` or the oracle's `orc_*`)."""
 
+    def _trace_buffer(self, iters: int, size: int) -> np.ndarray:
+        """Host array receiving the per-iteration root values (the product overrides it with page-locked memory)."""
+        return np.zeros((iters, size), dtype=np.float32)
+
     def __init__(self, lib: C.CDLL, prefix: str):
         self.lib = lib
         self.prefix = prefix
@@ -275,7 +279,7 @@ class Function:
             h, w = C.c_uint(), C.c_uint()
             ism = self._api._sym("value_dims")(self._h, C.byref(h), C.byref(w))
             size = h.value * w.value if ism else 1
-            out = np.zeros((iters, size), dtype=np.float32)
+            out = self._api._trace_buffer(iters, size)
             tptr = _fptr(out)
         pf = print_freq if print_freq is not None else iters + 1
         rc = self._api._sym(which)(self._h, n, names, ptrs, hs, ws, float(learn_rate), int(iters), int(pf), tptr)

@@ -1,5 +1,6 @@
 // capi.cpp — the C ABI of libcg_b200.so: include/cg_graph.h (graph level) and include/cg_matrix.h (the
 // reference's 26 matrix symbols). No torch types, no C++ types in any signature.
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -99,6 +100,17 @@ int cg_maximize(cg_function* f, int nargs, const char** names, const float** arg
     minimize(*n, pack_args(nargs, names, arg_vals, arg_h, arg_w), lr, iters, print_freq, trace, true);
   });
 }
+void* cg_host_alloc(size_t bytes) {
+  void* ptr = nullptr;
+  guard_rc([&] {
+    Runtime::get();
+    CG_CUDA(cudaHostAlloc(&ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  });
+  return ptr;
+}
+void cg_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
 int cg_minimize_async(cg_function* f, float lr, int iters) {
   return guard_rc([&] { minimize(*F(f), {}, lr, iters, 0, nullptr, false, /*reuse_inputs=*/true); });
 }
@@ -158,6 +170,26 @@ void cg_set_fix_act_grad(int v) { guard_rc([&] { Runtime::get().fix_act_grad = v
 void cg_set_fuse(int v) { guard_rc([&] { Runtime::get().fuse = v; }); }
 void cg_set_cuda_graph(int v) { guard_rc([&] { Runtime::get().use_graph = v; }); }
 void cg_set_strict_gemm_max(int v) { guard_rc([&] { Runtime::get().strict_gemm_max = v; }); }
+void cg_set_ew_jit_min(long long v) { guard_rc([&] { Runtime::get().ew_jit_min = v; }); }
+int cg_ew_jit_available(void) { return ew_jit_available() ? 1 : 0; }
+// Compiles (NVRTC -> sm_100a cubin, no GPU needed) a program that uses every opcode; returns the cubin size or -1.
+long long cg_ew_jit_selftest(void) {
+  long long bytes = -1;
+  guard_rc([&] {
+    EwProgram p{};
+    p.n = 1 << 20;
+    p.n_in = 3;
+    p.n_out = 2;
+    p.in_scalar_mask = 1u << 2;
+    const EwOpcode ops[] = {OP_LDR, OP_SIGMOID, OP_STR, OP_LDR, OP_SQ, OP_RSUB, OP_TANH, OP_STG, OP_ABS_M, OP_SGN_M, OP_ABS_S,
+                            OP_SGN_S, OP_ONE_MINUS, OP_NEG, OP_MULI, OP_ADD, OP_SUB, OP_MUL, OP_LDI, OP_MUL, OP_STG};
+    const int operand[] = {0, 0, 3, 1, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 1, 2, 1, 3, 0, 0, 1};
+    for (size_t k = 0; k < sizeof ops / sizeof ops[0]; k++) p.code[p.n_ins++] = ew_encode(ops[k], operand[k]);
+    bytes = (long long)ew_jit_compile_only(p);
+  });
+  return bytes;
+}
+void cg_set_io_graph(int v) { guard_rc([&] { Runtime::get().io_graph = v; }); }
 void cg_set_graph_streams(int v) {
   guard_rc([&] {
     Runtime& rt = Runtime::get();
@@ -170,7 +202,7 @@ void cg_set_graph_streams(int v) {
 static Plan& ensure_plan(Function& f, float lr) {
   Runtime& rt = Runtime::get();
   if (!f.plan || f.plan->lr != lr || f.plan->mode != rt.mode || f.plan->tf32 != rt.tf32 ||
-      f.plan->fix_act_grad != rt.fix_act_grad || f.plan->fuse != rt.fuse || f.plan->dp_epoch != rt.dp_epoch)
+      f.plan->fix_act_grad != rt.fix_act_grad || f.plan->fuse != rt.fuse || f.plan->dp_epoch != rt.dp_epoch || f.plan->ew_jit_min != rt.ew_jit_min)
     minimize(f, {}, lr, 0, 0, nullptr, true, true);  // compiles (and captures) without running an iteration
   return *f.plan;
 }
@@ -187,6 +219,7 @@ int cg_plan_stats_get(cg_function* f, float lr, cg_plan_stats* out) {
     out->arena_bytes = s.arena_bytes;
     out->gemm_flop_per_iter = s.gemm_flop_per_iter;
     out->ew_bytes_per_iter = s.ew_bytes_per_iter;
+    out->ew_specialised = s.ew_specialised;
   });
 }
 unsigned long long cg_launch_count(void) {
@@ -481,3 +514,4 @@ extern "C" int cg_debug_overlap(double out_ms[3]) {
     cudaStreamDestroy(s2);
   });
 }
+

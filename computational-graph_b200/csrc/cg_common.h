@@ -80,6 +80,16 @@ inline uint16_t ew_encode(EwOpcode op, int k = 0) { return (uint16_t)((op << 4) 
 // ------------------------------------------------------------------------------------------------
 void launch_ew_program(const EwProgram& p, cudaStream_t stream);
 
+// Plan-time specialisation of an elementwise program into straight-line sm_100a code (ew_jit.cpp, NVRTC).
+// ew_jit_get returns nullptr when libnvrtc is not available (the interpreter kernel above is used instead).
+struct EwKernel;
+bool ew_jit_available();
+const EwKernel* ew_jit_get(const EwProgram& p);
+void launch_ew_jit(const EwKernel* k, const EwProgram& p, cudaStream_t stream);
+std::string ew_jit_source(const EwProgram& p);
+size_t ew_jit_compile_only(const EwProgram& p);  // compiles without loading (no GPU needed); returns cubin bytes
+size_t ew_jit_cache_size();
+
 // dst (1 element) = reduce_sum(src[0..n)) / n   — the reference's `avg` (ops.rs:438-442, cpu/ops.cpp:138-145).
 // n <= kStrictReduceMax: one thread, sequential f32 sum (bit-identical to the reference's loop);
 // larger: float4 loads -> warp shuffle -> block -> ordered final pass (deterministic, pairwise rounding).

@@ -1,6 +1,8 @@
 // exec.cpp — `minimize` (src/optimize.rs:59-72) over a compiled plan: one CUDA-graph replay per iteration.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
+#include <functional>
 #include <unordered_map>
 
 #include "tape.h"
@@ -43,12 +45,19 @@ static void print_value(const Value& v) {
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 
-struct StepIO {
+// One node of the captured graph: the memory it reads / writes and how to enqueue it.
+struct CapNode {
   std::vector<const float*> reads, writes;
+  std::function<void(cudaStream_t)> launch;
+  // >= 0: pinned to a dedicated stream (0 = copy-in, 1 = copy-out, 2 = layout kernels of the inputs); -1: any compute
+  // stream. A node that waits for a late transfer must not sit on a compute stream: everything captured behind it on
+  // that stream would inherit the wait.
+  int lane = -1;
 };
 
-StepIO step_io(const Plan& p, const Step& s, const Runtime& rt) {
-  StepIO io;
+CapNode step_node(Plan& p, size_t index, const Runtime& rt) {
+  const Step& s = p.steps[index];
+  CapNode io;
   if (s.kind == Step::EW) {
     for (uint32_t k = 0; k < s.prog.n_in; k++) io.reads.push_back(s.prog.in[k]);
     for (uint32_t k = 0; k < s.prog.n_out; k++) io.writes.push_back(s.prog.out[k]);
@@ -59,6 +68,8 @@ StepIO step_io(const Plan& p, const Step& s, const Runtime& rt) {
     io.writes.push_back(p.vals[s.ins.dst].ptr);
     if (s.kind == Step::AVG) io.writes.push_back(rt.red_ws);  // the reduction workspace is a shared resource
   }
+  Plan* pp = &p;
+  io.launch = [pp, index](cudaStream_t st) { plan_launch_step(*pp, index, st); };
   return io;
 }
 
@@ -67,11 +78,13 @@ struct Loc {
   std::vector<int> readers;
 };
 
-void capture_dag(Plan& p, Runtime& rt) {
-  const int nstreams = rt.graph_streams;
-  const size_t n = p.steps.size();
-  if ((int)rt.side_streams.size() < nstreams) {
-    rt.side_streams.resize(nstreams, nullptr);
+constexpr int kIoLanes = 3;
+
+void capture_nodes(Plan& p, Runtime& rt, std::vector<CapNode>& nodes, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out) {
+  const int nstreams = rt.graph_streams > 0 ? rt.graph_streams : 0;
+  const size_t n = nodes.size();
+  if ((int)rt.side_streams.size() < nstreams + kIoLanes) {
+    rt.side_streams.resize(nstreams + kIoLanes, nullptr);
     for (auto& st : rt.side_streams)
       if (!st) CG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   }
@@ -80,11 +93,11 @@ void capture_dag(Plan& p, Runtime& rt) {
     CG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     p.events.push_back(e);
   }
-  // dependencies from memory locations
+  // dependencies from memory locations (RAW, WAR, WAW), in program order
   std::unordered_map<const float*, Loc> loc;
   std::vector<std::vector<int>> deps(n);
   for (size_t i = 0; i < n; i++) {
-    StepIO io = step_io(p, p.steps[i], rt);
+    const CapNode& io = nodes[i];
     auto add = [&](int d) {
       if (d >= 0 && d != (int)i && std::find(deps[i].begin(), deps[i].end(), d) == deps[i].end()) deps[i].push_back(d);
     };
@@ -101,10 +114,11 @@ void capture_dag(Plan& p, Runtime& rt) {
       l.readers.clear();
     }
   }
-  // stream 0 is the capturing (origin) stream
+  // streams: [0] the capturing (origin) stream, [1, nstreams] compute side streams, then the transfer lanes
   std::vector<cudaStream_t> streams{rt.stream};
-  for (int k = 0; k < nstreams; k++) streams.push_back(rt.side_streams[k]);
-  std::vector<int> stream_last(streams.size(), -1), step_stream(n, 0);
+  for (int k = 0; k < nstreams + kIoLanes; k++) streams.push_back(rt.side_streams[k]);
+  const size_t ncompute = (size_t)nstreams + 1;
+  std::vector<int> stream_last(streams.size(), -1), node_stream(n, 0);
   std::vector<char> forked(streams.size(), 0);
   forked[0] = 1;
   cudaEvent_t fork_ev = p.events[n];
@@ -113,18 +127,22 @@ void capture_dag(Plan& p, Runtime& rt) {
     CG_CUDA(cudaEventRecord(fork_ev, rt.stream));
     for (size_t i = 0; i < n; i++) {
       int chosen = -1;
-      // 1. a stream whose most recent node is one of our dependencies: no extra edge, no false dependency
-      for (size_t s = 0; s < streams.size(); s++)
-        if (stream_last[s] >= 0 && std::find(deps[i].begin(), deps[i].end(), stream_last[s]) != deps[i].end())
-          if (chosen < 0 || stream_last[s] > stream_last[chosen]) chosen = (int)s;
-      // 2. an unused stream; 3. the stream that has been idle longest
-      if (chosen < 0)
-        for (size_t s = 0; s < streams.size() && chosen < 0; s++)
-          if (stream_last[s] < 0) chosen = (int)s;
-      if (chosen < 0) {
-        chosen = 0;
-        for (size_t s = 1; s < streams.size(); s++)
-          if (stream_last[s] < stream_last[chosen]) chosen = (int)s;
+      if (nodes[i].lane >= 0) {
+        chosen = (int)ncompute + nodes[i].lane;
+      } else {
+        // 1. a stream whose most recent node is one of our dependencies: no extra edge, no false dependency
+        for (size_t s = 0; s < ncompute; s++)
+          if (stream_last[s] >= 0 && std::find(deps[i].begin(), deps[i].end(), stream_last[s]) != deps[i].end())
+            if (chosen < 0 || stream_last[s] > stream_last[chosen]) chosen = (int)s;
+        // 2. an unused stream; 3. the stream that has been idle longest
+        if (chosen < 0)
+          for (size_t s = 0; s < ncompute && chosen < 0; s++)
+            if (stream_last[s] < 0) chosen = (int)s;
+        if (chosen < 0) {
+          chosen = 0;
+          for (size_t s = 1; s < ncompute; s++)
+            if (stream_last[s] < stream_last[chosen]) chosen = (int)s;
+        }
       }
       cudaStream_t st = streams[chosen];
       if (!forked[chosen]) {
@@ -132,11 +150,11 @@ void capture_dag(Plan& p, Runtime& rt) {
         forked[chosen] = 1;
       }
       for (int d : deps[i])
-        if (step_stream[d] != chosen) CG_CUDA(cudaStreamWaitEvent(st, p.events[d], 0));
-      plan_launch_step(p, i, st);
+        if (node_stream[d] != chosen) CG_CUDA(cudaStreamWaitEvent(st, p.events[d], 0));
+      nodes[i].launch(st);
       CG_CUDA(cudaEventRecord(p.events[i], st));
       stream_last[chosen] = (int)i;
-      step_stream[i] = chosen;
+      node_stream[i] = chosen;
     }
     for (size_t s = 1; s < streams.size(); s++)
       if (stream_last[s] >= 0) CG_CUDA(cudaStreamWaitEvent(rt.stream, p.events[stream_last[s]], 0));
@@ -146,8 +164,128 @@ void capture_dag(Plan& p, Runtime& rt) {
     if (g) cudaGraphDestroy(g);
     throw;
   }
-  CG_CUDA(cudaStreamEndCapture(rt.stream, &p.graph));
-  CG_CUDA(cudaGraphInstantiate(&p.graph_exec, p.graph, 0));
+  CG_CUDA(cudaStreamEndCapture(rt.stream, graph_out));
+  CG_CUDA(cudaGraphInstantiate(exec_out, *graph_out, 0));
+}
+
+void capture_dag(Plan& p, Runtime& rt) {
+  std::vector<CapNode> nodes;
+  for (size_t i = 0; i < p.steps.size(); i++) nodes.push_back(step_node(p, i, rt));
+  capture_nodes(p, rt, nodes, &p.graph, &p.graph_exec);
+}
+
+// The node a stream capture has just appended (the only dependency of whatever is enqueued next on `st`).
+cudaGraphNode_t last_captured_node(cudaStream_t st) {
+  cudaStreamCaptureStatus status;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t ndeps = 0;
+  CG_CUDA(cudaStreamGetCaptureInfo(st, &status, nullptr, nullptr, &deps, &ndeps));
+  if (status != cudaStreamCaptureStatusActive || ndeps != 1) throw Error("internal: cannot identify the captured copy node");
+  return deps[0];
+}
+
+bool is_pinned_host(const void* ptr) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost;
+}
+
+const Arg* find_arg(const std::vector<Arg>& args, const Function* f) {
+  const Arg* a = nullptr;
+  for (const Arg& c : args)
+    if (c.name == f->body->name) a = &c;
+  if (!a) throw Error("panic: missing arg `" + f->body->name + "`");
+  const bool is_matrix = !(a->h == 0 && a->w == 0);
+  if (is_matrix != f->value.is_matrix) throw Error("panic: Cannot copy mismatched Constants.");
+  if (is_matrix && (a->h != f->value.h || a->w != f->value.w)) throw Error("ERROR: copy_matrix: dims differ");
+  return a;
+}
+
+// The transfers of one call can live inside the graph when every host buffer is page-locked (a copy node from
+// pageable memory would be staged synchronously by the driver and could not overlap anything).
+bool io_graph_eligible(const Plan& p, const Runtime& rt, const std::vector<Arg>& args, const float* trace) {
+  if (!rt.use_graph || !rt.io_graph || rt.graph_streams <= 0 || p.steps.empty() || p.input_leaves.empty()) return false;
+  for (Function* f : p.input_leaves)
+    if (!is_pinned_host(find_arg(args, f)->vals)) return false;
+  return !trace || is_pinned_host(trace);
+}
+
+void launch_io_graph(Plan& p, Runtime& rt, const std::vector<Arg>& args, float* trace) {
+  IoGraph& g = p.io[trace ? 1 : 0];
+  const size_t nin = p.input_leaves.size();
+  std::vector<const float*> src(nin);
+  for (size_t i = 0; i < nin; i++) src[i] = find_arg(args, p.input_leaves[i])->vals;
+  if (!g.exec) {
+    if (p.io_staging.size() < nin) p.io_staging.resize(nin);
+    g.h2d_nodes.assign(nin, nullptr);
+    g.h2d_src = src;
+    g.h2d_dst.assign(nin, nullptr);
+    g.h2d_bytes.assign(nin, 0);
+    g.d2h_dst = trace;
+    std::vector<CapNode> nodes;
+    IoGraph* gp = &g;
+    Plan* pp = &p;
+    auto d2h = [&]() {
+      CapNode c;
+      c.lane = 1;
+      c.reads.push_back(p.root_ptr);
+      c.launch = [gp, pp](cudaStream_t st) {
+        CG_CUDA(cudaMemcpyAsync(gp->d2h_dst, pp->root_ptr, pp->root_n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        gp->d2h_node = last_captured_node(st);
+      };
+      return c;
+    };
+    // a leaf root is read BEFORE this iteration's update overwrites it (Q12)
+    if (trace && p.root_is_leaf) nodes.push_back(d2h());
+    for (size_t i = 0; i < nin; i++) {
+      Value& v = p.input_leaves[i]->value;
+      const size_t n = v.size();
+      const bool direct = !v.is_matrix || v.h == 1 || v.w == 1;  // both layouts coincide
+      if (!direct && (!p.io_staging[i] || p.io_staging[i]->n < n)) p.io_staging[i] = DevBuf::alloc(n);
+      g.h2d_dst[i] = direct ? v.buf->ptr : p.io_staging[i]->ptr;
+      g.h2d_bytes[i] = n * sizeof(float);
+      CapNode c;
+      c.lane = 0;  // one copy-in lane: the inputs arrive in the order the forward pass consumes them
+      c.writes.push_back(g.h2d_dst[i]);
+      c.launch = [gp, i](cudaStream_t st) {
+        CG_CUDA(cudaMemcpyAsync(gp->h2d_dst[i], gp->h2d_src[i], gp->h2d_bytes[i], cudaMemcpyHostToDevice, st));
+        gp->h2d_nodes[i] = last_captured_node(st);
+      };
+      nodes.push_back(std::move(c));
+      if (!direct) {
+        CapNode t;
+        t.lane = 2;
+        t.reads.push_back(g.h2d_dst[i]);
+        t.writes.push_back(v.buf->ptr);
+        const float* from = g.h2d_dst[i];
+        float* to = v.buf->ptr;
+        const unsigned h = v.h, w = v.w;
+        t.launch = [from, to, h, w](cudaStream_t st) { launch_rowmajor_to_colmajor(from, to, h, w, st); };
+        nodes.push_back(std::move(t));
+        g.layout_kernels++;
+      }
+    }
+    for (size_t i = 0; i < p.steps.size(); i++) nodes.push_back(step_node(p, i, rt));
+    if (trace && !p.root_is_leaf) nodes.push_back(d2h());
+    capture_nodes(p, rt, nodes, &g.graph, &g.exec);
+  } else {
+    for (size_t i = 0; i < nin; i++)
+      if (g.h2d_src[i] != src[i]) {
+        CG_CUDA(cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.h2d_nodes[i], g.h2d_dst[i], src[i], g.h2d_bytes[i],
+                                                   cudaMemcpyHostToDevice));
+        g.h2d_src[i] = src[i];
+      }
+    if (trace && g.d2h_dst != trace) {
+      CG_CUDA(cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.d2h_node, trace, p.root_ptr, p.root_n * sizeof(float),
+                                                 cudaMemcpyDeviceToHost));
+      g.d2h_dst = trace;
+    }
+  }
+  CG_CUDA(cudaGraphLaunch(g.exec, rt.stream));
+  rt.launches += p.steps.size() + g.layout_kernels;
 }
 
 }  // namespace
@@ -156,12 +294,25 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
               bool synchronize, bool reuse_inputs) {
   Runtime& rt = Runtime::get();
   if (!f.plan || f.plan->lr != lr || f.plan->mode != rt.mode || f.plan->tf32 != rt.tf32 ||
-      f.plan->fix_act_grad != rt.fix_act_grad || f.plan->fuse != rt.fuse || f.plan->dp_epoch != rt.dp_epoch) {
+      f.plan->fix_act_grad != rt.fix_act_grad || f.plan->fuse != rt.fuse || f.plan->dp_epoch != rt.dp_epoch || f.plan->ew_jit_min != rt.ew_jit_min) {
     f.plan.reset();
     f.plan = build_plan(f, lr);
   }
   Plan& p = *f.plan;
-  if (!reuse_inputs) upload_inputs(p, args);
+  static const bool dbg = getenv("CG_DEBUG_TIMING") != nullptr;
+  cudaEvent_t dbg_ev[3] = {};
+  double dbg_t0 = 0;
+  auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  if (dbg) {
+    for (auto& e : dbg_ev) cudaEventCreate(&e);
+    dbg_t0 = wall();
+    cudaEventRecord(dbg_ev[0], rt.stream);
+  }
+  // One iteration whose host transfers ride inside the graph (pinned buffers only); otherwise: upload, then loop.
+  const bool io = !reuse_inputs && iters >= 1 && (iters == 1 || !trace) && io_graph_eligible(p, rt, args, trace);
+  if (!reuse_inputs && !io) upload_inputs(p, args);
+  if (dbg) cudaEventRecord(dbg_ev[1], rt.stream);
+  const double dbg_t1 = dbg ? wall() : 0;
   for (Function* leaf : p.param_leaves) leaf->value.summary_valid = false;  // device values diverge from here on
   f.value.summary_valid = false;
   f.value.defined = true;
@@ -185,9 +336,14 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
   float* trace_dev = nullptr;
   const bool direct_trace = trace && iters == 1;  // one iteration: read the root value straight back
   if (trace && iters > 1) CG_CUDA(cudaMalloc(&trace_dev, (size_t)iters * p.root_n * sizeof(float)));
-  if (direct_trace && p.root_is_leaf)
+  if (direct_trace && p.root_is_leaf && !io)
     CG_CUDA(cudaMemcpyAsync(trace, p.root_ptr, p.root_n * sizeof(float), cudaMemcpyDeviceToHost, rt.stream));
   for (int i = 0; i < iters; i++) {
+    if (i == 0 && io) {
+      launch_io_graph(p, rt, args, trace);
+      if (print_freq > 0 && (i + 1) % print_freq == 0) print_value(f.value);
+      continue;
+    }
     // the traced value is the forward value of iteration i, i.e. before its update (Q12)
     if (trace_dev && p.root_is_leaf)
       CG_CUDA(cudaMemcpyAsync(trace_dev + (size_t)i * p.root_n, p.root_ptr, p.root_n * sizeof(float),
@@ -201,7 +357,7 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
     if (print_freq > 0 && (i + 1) % print_freq == 0) print_value(f.value);
   }
   if (direct_trace) {
-    if (!p.root_is_leaf)
+    if (!p.root_is_leaf && !io)
       CG_CUDA(cudaMemcpyAsync(trace, p.root_ptr, p.root_n * sizeof(float), cudaMemcpyDeviceToHost, rt.stream));
     CG_CUDA(cudaStreamSynchronize(rt.stream));
   }
@@ -211,7 +367,18 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
     CG_CUDA(cudaStreamSynchronize(rt.stream));
     CG_CUDA(cudaFree(trace_dev));
   }
+  const double dbg_t2 = dbg ? wall() : 0;
   if (synchronize) CG_CUDA(cudaStreamSynchronize(rt.stream));
+  if (dbg) {
+    cudaEventRecord(dbg_ev[2], rt.stream);
+    cudaEventSynchronize(dbg_ev[2]);
+    float up = 0, run = 0;
+    cudaEventElapsedTime(&up, dbg_ev[0], dbg_ev[1]);
+    cudaEventElapsedTime(&run, dbg_ev[1], dbg_ev[2]);
+    fprintf(stderr, "[cg timing] io=%d iters=%d host: upload-enqueue %.3f ms, loop-enqueue %.3f ms, sync %.3f ms | device: upload %.3f ms, loop %.3f ms\n",
+            (int)io, iters, dbg_t1 - dbg_t0, dbg_t2 - dbg_t1, wall() - dbg_t2, up, run);
+    for (auto& e : dbg_ev) cudaEventDestroy(e);
+  }
 }
 
 }  // namespace cg

@@ -38,6 +38,8 @@ void Runtime::init() {
   if (const char* s = getenv("CG_FUSE")) fuse = atoi(s);
   if (const char* s = getenv("CG_CUDA_GRAPH")) use_graph = atoi(s);
   if (const char* s = getenv("CG_GRAPH_STREAMS")) graph_streams = atoi(s);
+  if (const char* s = getenv("CG_IO_GRAPH")) io_graph = atoi(s);
+  if (const char* s = getenv("CG_EW_JIT_MIN")) ew_jit_min = atoll(s);
 }
 
 static void fill_device(float* ptr, size_t n, float v) {
@@ -162,7 +164,11 @@ static Value summary_of(const Value& v) {
 
 Function* clone_function(const Function& f) {
   auto* g = new Function();
-  g->value = clone_value(f.value);
+  // Constants and Inputs are never written by the loop (only Params are, optimize.rs:149-152), so their clones can
+  // share one device buffer: the reference's per-clone copy (matrix.rs:100-106) is unobservable for them, and an
+  // Input named once in `args` is then uploaded once, not once per use site. Params keep a private copy (Q1).
+  const bool read_only_leaf = f.body && (f.body->kind == Kind::Constant || f.body->kind == Kind::Input);
+  g->value = read_only_leaf ? f.value : clone_value(f.value);
   g->has_params = f.has_params;
   g->body = f.body;
   return g;

@@ -75,6 +75,8 @@ struct Runtime {
   int fuse = 1;          // 0 = one kernel per IR instruction (debug / ablation)
   int use_graph = 1;     // capture each iteration as a CUDA graph
   int graph_streams = 4; // side streams used when an iteration is captured as a DAG (0 = single stream)
+  long long ew_jit_min = 32768;  // elementwise programs over >= this many elements are specialised (ew_jit.cpp); < 0: never
+  int io_graph = 1;      // put the H2D / D2H transfers of a `minimize(&args, lr, 1)` call inside the iteration graph
   std::vector<cudaStream_t> side_streams;
   int dp_epoch = 0;      // bumped whenever the data-parallel configuration changes (invalidates plans)
   int strict_gemm_max = 64;  // products with max(m,n,k) <= this use the bit-exact strict kernel

@@ -20,6 +20,10 @@ namespace cg {
 Plan::~Plan() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (graph) cudaGraphDestroy(graph);
+  for (IoGraph& g : io) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
   for (cudaEvent_t e : events) cudaEventDestroy(e);
 }
 
@@ -39,7 +43,8 @@ struct Builder {
   int fix_act_grad;
   std::unordered_map<const Function*, int> leaf_cur;  // leaf use site -> current SSA version
   std::unordered_map<const Expr*, int> node_val;      // shared body -> forward value
-  std::unordered_set<const Function*> seen_inputs, seen_params;
+  std::unordered_set<const Function*> seen_params;
+  std::unordered_set<const float*> seen_input_bufs;
 
   bool dp = false;
 
@@ -80,7 +85,8 @@ struct Builder {
     if (!f.value.buf) throw Error("leaf without device storage");
     int id = new_fixed(shape_of(f), f.value.buf);
     leaf_cur[&f] = id;
-    if (f.body->kind == Kind::Input && seen_inputs.insert(&f).second) p.input_leaves.push_back(&f);
+    // clones of an Input share its buffer (graph.cpp clone_function): one upload per distinct buffer
+    if (f.body->kind == Kind::Input && seen_input_bufs.insert(f.value.buf->ptr).second) p.input_leaves.push_back(&f);
     if (f.body->kind == Kind::Param && seen_params.insert(&f).second) p.param_leaves.push_back(&f);
     return id;
   }
@@ -737,6 +743,10 @@ void finalize_steps(Plan& p) {
       for (size_t k = 0; k < s.ew.imm.size(); k++) pr.imm[k] = s.ew.imm[k];
       for (size_t k = 0; k < s.ew.code.size(); k++) pr.code[k] = s.ew.code[k];
       p.stats.ew_groups++;
+      if (p.ew_jit_min >= 0 && (long long)pr.n >= p.ew_jit_min) {
+        s.jit = ew_jit_get(pr);
+        if (s.jit) p.stats.ew_specialised++;
+      }
     } else if (s.kind == Step::GEMM) {
       const Shape &as = p.vals[s.ins.a].sh, &cs = p.vals[s.ins.dst].sh;
       const double k = s.ins.ta ? as.h : as.w;
@@ -761,6 +771,7 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr) {
   p.fix_act_grad = rt.fix_act_grad;
   p.fuse = rt.fuse;
   p.dp_epoch = rt.dp_epoch;
+  p.ew_jit_min = rt.ew_jit_min;
 
   Builder b(p, lr, rt.fix_act_grad);
   b.forward(root);
@@ -812,7 +823,10 @@ void plan_launch_step(Plan& p, size_t index, cudaStream_t stream) {
   Step& s = p.steps[index];
   {
     switch (s.kind) {
-      case Step::EW: launch_ew_program(s.prog, stream); break;
+      case Step::EW:
+        if (s.jit) launch_ew_jit(s.jit, s.prog, stream);
+        else launch_ew_program(s.prog, stream);
+        break;
       case Step::AVG: {
         const Val& a = p.vals[s.ins.a];
         launch_reduce_avg(a.ptr, a.sh.n(), p.vals[s.ins.dst].ptr, rt.red_ws, stream);

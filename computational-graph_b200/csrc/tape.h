@@ -67,12 +67,28 @@ struct Step {
   EwGroup ew;
   Instr ins;  // AVG / GEMM / ALLREDUCE
   EwProgram prog;  // EW, filled after memory assignment
+  const EwKernel* jit = nullptr;  // EW: the program specialised into straight-line code (large domains only)
 };
 
 struct PlanStats {
   size_t tape_instrs = 0, live_instrs = 0, ew_groups = 0, gemms = 0, gemms_fused_sgd = 0, reduces = 0;
-  size_t arena_bytes = 0, kernels_per_iter = 0;
+  size_t arena_bytes = 0, kernels_per_iter = 0, ew_specialised = 0;
   double gemm_flop_per_iter = 0.0, ew_bytes_per_iter = 0.0;
+};
+
+// The iteration graph with the host transfers of one `minimize(&args, lr, 1)` call inside it: H2D copies of the
+// Input values (pinned host memory -> staging), their layout kernels, the iteration, and the D2H read of the root
+// value — so the copies overlap the compute instead of preceding / following it (exec.cpp).
+struct IoGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<cudaGraphNode_t> h2d_nodes;  // one per input leaf, Plan::input_leaves order
+  std::vector<const float*> h2d_src;
+  std::vector<float*> h2d_dst;
+  std::vector<size_t> h2d_bytes;
+  cudaGraphNode_t d2h_node = nullptr;
+  float* d2h_dst = nullptr;
+  size_t layout_kernels = 0;
 };
 
 struct Plan {
@@ -83,6 +99,7 @@ struct Plan {
   PlanStats stats;
   float lr = 0.0f;
   int mode = 0, tf32 = 0, fix_act_grad = 0, fuse = 1, dp_epoch = 0;
+  long long ew_jit_min = -1;
   bool root_is_leaf = false;
   float* root_ptr = nullptr;
   size_t root_n = 1;
@@ -90,7 +107,9 @@ struct Plan {
   std::vector<Function*> param_leaves;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
-  std::vector<cudaEvent_t> events;  // one per step (+1 fork event) for the multi-stream capture
+  std::vector<cudaEvent_t> events;  // one per captured node (+1 fork event) for the multi-stream capture
+  IoGraph io[2];                    // [0] without, [1] with the D2H read of the root value
+  std::vector<BufRef> io_staging;   // row-major landing buffer per matrix input
   ~Plan();
 };
 

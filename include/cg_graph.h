@@ -59,6 +59,12 @@ int cg_minimize(cg_function *f, int nargs, const char **names, const float **arg
                 const unsigned *arg_w, float learn_rate, int iters, int print_freq, float *trace);
 int cg_maximize(cg_function *f, int nargs, const char **names, const float **arg_vals, const unsigned *arg_h,
                 const unsigned *arg_w, float learn_rate, int iters, int print_freq, float *trace);
+/* Page-locked host memory for `args` values and `trace` buffers. When every host buffer of a
+ * `cg_minimize(..., iters = 1, ...)` call is page-locked (these, cudaHostAlloc/cudaHostRegister, torch pin_memory),
+ * the H2D copies of the inputs and the D2H read of the root value become nodes of the iteration's CUDA graph and
+ * overlap the compute; pageable buffers are copied before / after it as the reference does. */
+void *cg_host_alloc(size_t bytes);
+void cg_host_free(void *ptr);
 /* Same loop, enqueued on the library stream without waiting (device-resident timing: bench.py). */
 int cg_minimize_async(cg_function *f, float learn_rate, int iters);
 int cg_synchronize(void);
@@ -83,12 +89,19 @@ void cg_set_fuse(int on);             /* 0: one kernel per tape instruction (abl
 void cg_set_cuda_graph(int on);       /* 0: launch kernels eagerly instead of replaying a CUDA graph */
 void cg_set_strict_gemm_max(int dim); /* products with max(m,n,k) <= dim use the bit-exact kernel */
 void cg_set_graph_streams(int n);     /* side streams of the per-iteration CUDA graph (0: one linear stream) */
+/* Elementwise programs over >= min_elems elements are unrolled into straight-line sm_100a code at plan time
+ * (NVRTC; bit-identical to the interpreter kernel, which keeps the smaller ones). < 0: never. Default 32768. */
+void cg_set_ew_jit_min(long long min_elems);
+int cg_ew_jit_available(void);
+long long cg_ew_jit_selftest(void);   /* compiles a program using every opcode; cubin bytes or -1 (no GPU needed) */
+void cg_set_io_graph(int on);         /* 0: never put host transfers inside the iteration graph */
 
 /* ---- introspection -------------------------------------------------------------------------------- */
 typedef struct {
   unsigned long long tape_instrs, live_instrs, kernels_per_iter, ew_kernels, gemms, gemms_fused_sgd, reduces;
   unsigned long long arena_bytes;
   double gemm_flop_per_iter, ew_bytes_per_iter;
+  unsigned long long ew_specialised; /* elementwise kernels compiled to straight-line code (cg_set_ew_jit_min) */
 } cg_plan_stats;
 int cg_plan_stats_get(cg_function *f, float learn_rate, cg_plan_stats *out); /* compiles the plan if needed */
 unsigned long long cg_launch_count(void); /* kernels launched by this library so far */

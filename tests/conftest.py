@@ -36,4 +36,6 @@ def cg():
     api.set_fuse(True)
     api.set_cuda_graph(True)
     api.set_strict_gemm_max(64)
+    api.set_ew_jit_min(32768)
+    api.set_io_graph(True)
     return api

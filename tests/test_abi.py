@@ -60,3 +60,14 @@ def test_product_package_never_imports_the_oracle():
             if fn.endswith((".py", ".cpp", ".cu", ".h", ".cuh")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "liboracle" not in text and "import oracle" not in text and "from oracle" not in text, fn
+
+
+def test_elementwise_specialiser_compiles_for_sm_100a_without_a_gpu(lib):
+    """ew_jit.cpp: a program using every opcode is unrolled to CUDA C and compiled to an sm_100a cubin by NVRTC."""
+    lib.cg_ew_jit_available.restype = C.c_int
+    if not lib.cg_ew_jit_available():
+        pytest.skip("libnvrtc is not installed")
+    lib.cg_ew_jit_selftest.restype = C.c_longlong
+    lib.cg_last_error.restype = C.c_char_p
+    size = lib.cg_ew_jit_selftest()
+    assert size > 1000, lib.cg_last_error()

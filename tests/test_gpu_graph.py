@@ -204,3 +204,117 @@ def test_lstm_tf32_tensor_core_path(cg, oracle):
             assert rel_err(lg[k], lo[k]) < 1e-3, k
     finally:
         oracle.set_mode("exact")
+
+
+def test_host_transfers_inside_the_iteration_graph(cg, oracle):
+    """`minimize(&args, lr, 1)` with page-locked host buffers runs H2D + layout + iteration + D2H as ONE graph
+    (exec.cpp launch_io_graph). Results must be bit-identical to the pageable path (upload, then iterate), across
+    calls that change the host pointers and the input values, and equal to the oracle."""
+    rng = np.random.default_rng(11)
+    B, I, H = 8, 6, 5
+    wv = rng.uniform(-1, 1, (I, H)).astype(np.float32)
+    bv = rng.uniform(-1, 1, (B, H)).astype(np.float32)
+    xs = [rng.uniform(-1, 1, (B, I)).astype(np.float32) for _ in range(4)]
+    ts = [rng.uniform(-1, 1, (B, H)).astype(np.float32) for _ in range(4)]
+
+    def build(api):
+        x = api.Function.input("x", [B, I])
+        t = api.Function.input("t", [B, H])
+        s = api.Function.input("s", [])  # a scalar input rides the same path (no layout kernel)
+        w = api.Function.param("w", api.Constant(wv))
+        b = api.Function.param("b", api.Constant(bv))
+        return ((api.dot(x, w) + b).tanh() * s - t).sq()
+
+    def run(api, pinned, io):
+        if api is cg:
+            cg.set_io_graph(io)
+        f = build(api)
+        traces = []
+        for k in range(4):
+            if pinned:
+                # fresh page-locked buffers on every call for k < 2 (pointer update), the same ones afterwards
+                xa, ta = cg.pinned_empty((B, I)), cg.pinned_empty((B, H))
+                xa[...] = xs[k]
+                ta[...] = ts[k]
+                keep.append((xa, ta))
+            else:
+                xa, ta = xs[k], ts[k]
+            args = {"x": api.Constant(xa), "t": api.Constant(ta), "s": api.Constant.Scalar(0.5 + k)}
+            traces.append(np.array(f.minimize(args, 0.05, 1, trace=True)))
+        more = np.array(f.minimize(args, 0.05, 3, trace=True))  # iters > 1: upload once, then the plain graph
+        return traces, more, leaves_dict(f)
+
+    keep = []
+    launches0 = cg.launch_count()
+    try:
+        got = run(cg, True, True)
+        io_launches = cg.launch_count() - launches0
+        ref = run(cg, False, True)       # pageable buffers: never eligible
+        off = run(cg, True, False)       # page-locked but switched off
+    finally:
+        cg.set_io_graph(True)
+    want = run(oracle, False, False)
+    assert io_launches > 0
+    for other in (ref, off):
+        for a, b in zip(got[0], other[0]):
+            assert np.array_equal(a.view(np.int32), b.view(np.int32))
+        assert np.array_equal(got[1].view(np.int32), other[1].view(np.int32))
+        for k in got[2]:
+            assert np.array_equal(got[2][k].view(np.int32), other[2][k].view(np.int32)), k
+    for a, b in zip(got[0], want[0]):
+        assert rel_err(a, b) < 1e-5
+    for k in got[2]:
+        assert rel_err(got[2][k], want[2][k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("shape", [(301, 303), (256, 512)])
+def test_specialised_elementwise_kernels_equal_the_interpreter(cg, shape):
+    """ew_jit.cpp: the straight-line kernel NVRTC compiles from a fused program is bit-identical to the bytecode
+    interpreter running the same program — C2 graph (sigmoid, tanh, abs, SGD) on a ragged and an aligned size."""
+    rng = np.random.default_rng(5)
+    wv = rng.uniform(-1, 1, shape).astype(np.float32)
+    vv = rng.uniform(-1, 1, shape).astype(np.float32)
+
+    def run(jit_min):
+        cg.set_ew_jit_min(jit_min)
+        W = cg.Function.param("W", cg.Constant(wv))
+        V = cg.Function.param("V", cg.Constant(vv))
+        f = (W.sigmoid() - V.sq()).tanh() + W.abs()
+        st = cg.plan_stats(f, 0.01)
+        tr = np.array(f.minimize({}, 0.01, 4, trace=True))
+        return st, tr, leaves_dict(f)
+
+    try:
+        st_j, tr_j, lv_j = run(0)
+        st_i, tr_i, lv_i = run(-1)
+    finally:
+        cg.set_ew_jit_min(32768)
+    assert st_j["ew_specialised"] == st_j["ew_kernels"] > 0 and st_i["ew_specialised"] == 0
+    assert np.array_equal(tr_j.view(np.int32), tr_i.view(np.int32))
+    for k in lv_j:
+        assert np.array_equal(lv_j[k].view(np.int32), lv_i[k].view(np.int32)), k
+
+
+def test_specialised_elementwise_kernels_lstm_dag(cg, oracle):
+    """Every elementwise group of a dag-mode LSTM on the specialised path: bit-identical to the interpreter and
+    within 1e-5 of the oracle (transcendentals)."""
+    cg.set_mode("dag")
+    oracle.set_mode("dag")
+    try:
+        out = []
+        for jit_min in (0, -1):
+            cg.set_ew_jit_min(jit_min)
+            f = readme_lstm(cg, 24, T=3, seed=77, batch=40, d_in=16)
+            out.append((np.array(f.minimize({}, 0.01, 3, trace=True)), leaves_dict(f), cg.plan_stats(f, 0.01)))
+        fo = readme_lstm(oracle, 24, T=3, seed=77, batch=40, d_in=16)
+        to = fo.minimize({}, 0.01, 3, trace=True)
+        lo = leaves_dict(fo)
+    finally:
+        cg.set_ew_jit_min(32768)
+        oracle.set_mode("exact")
+    assert out[0][2]["ew_specialised"] > 0
+    assert np.array_equal(out[0][0].view(np.int32), out[1][0].view(np.int32))
+    for k in out[0][1]:
+        assert np.array_equal(out[0][1][k].view(np.int32), out[1][1][k].view(np.int32)), k
+        assert rel_err(out[0][1][k], lo[k]) < 1e-5, k
+    assert rel_err(out[0][0], to) < 1e-5

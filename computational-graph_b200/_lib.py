@@ -49,7 +49,7 @@ class ProductApi(Api):
     def __init__(self, lib: C.CDLL):
         super().__init__(lib, "cg_")
         for name in ("set_tf32", "set_fix_act_grad", "set_fuse", "set_cuda_graph", "set_strict_gemm_max",
-                     "set_graph_streams", "set_io_graph"):
+                     "set_graph_streams", "set_io_graph", "set_tf32_pair"):
             fn = self._sym(name)
             fn.restype, fn.argtypes = None, [C.c_int]
         lib.cg_launch_count.restype = C.c_ulonglong
@@ -111,6 +111,7 @@ class ProductApi(Api):
     def set_strict_gemm_max(self, dim: int): self.lib.cg_set_strict_gemm_max(int(dim))
     def set_graph_streams(self, n: int): self.lib.cg_set_graph_streams(int(n))
     def set_ew_jit_min(self, min_elems: int): self.lib.cg_set_ew_jit_min(int(min_elems))
+    def set_tf32_pair(self, on: bool): self.lib.cg_set_tf32_pair(int(on))
     def set_io_graph(self, on: bool): self.lib.cg_set_io_graph(int(on))
     def set_device(self, dev: int): self._check(self.lib.cg_set_device(int(dev)))
     def launch_count(self) -> int: return int(self.lib.cg_launch_count())

@@ -189,6 +189,12 @@ long long cg_ew_jit_selftest(void) {
   });
   return bytes;
 }
+void cg_set_tf32_pair(int v) {
+  guard_rc([&] {
+    gemm_tf32_set_pair(v);
+    Runtime::get().dp_epoch++;  // captured graphs hold the kernel choice: invalidate cached plans
+  });
+}
 void cg_set_io_graph(int v) { guard_rc([&] { Runtime::get().io_graph = v; }); }
 void cg_set_graph_streams(int v) {
   guard_rc([&] {

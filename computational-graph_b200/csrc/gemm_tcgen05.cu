@@ -31,7 +31,6 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 32;          // 32 floats = one 128-byte swizzle row
 constexpr int UMMA_K = 8;       // kind::tf32: 32 bytes of K per instruction
-constexpr int STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int NUM_THREADS = 192;
 
@@ -128,9 +127,12 @@ struct TuneParams {
   uint32_t mn_lbo, mn_sbo, mn_step;  // MN-major operand
   uint32_t mn_layout;                // descriptor layout type of the MN-major operand
   uint32_t mn_chunked;               // 1: fetch MN-major tiles as 2-D boxes {32, BK}, one per 32-wide chunk
+  uint32_t pair_peer_arrives;        // pair kernel: the peer's producer also arrives on the leader's full barrier
+  uint32_t pair_small_only;          // pair kernel bring-up: fetch B in small boxes only
+  uint32_t debug_clock;              // block 0 prints SM cycles / nanoseconds spent in its main loop (clock under load)
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      float* __restrict__ C, int m, int n, int k, int ldc, int epi_mode, float lr, TuneParams tp) {
@@ -212,6 +214,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      long long c0 = 0, t0 = 0;
+      if (tp.debug_clock && blockIdx.x == 0) {
+        c0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
@@ -233,6 +240,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         tcgen05_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
+      }
+      if (tp.debug_clock && blockIdx.x == 0) {
+        long long c1 = clock64(), t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        printf("[gemm_tf32 clock] issue loop: %lld cycles in %lld ns = %.0f MHz (k-blocks %d)\n", c1 - c0, t1 - t0,
+               (double)(c1 - c0) * 1e3 / (double)(t1 - t0), num_kb);
       }
     }
   } else {
@@ -283,6 +296,263 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// =====================================================================================================================
+// CTA-pair kernel (cta_group::2): two SMs of one TPC compute a 256 x W tile together. CTA r of the pair stages rows
+// [m0 + 128 r, +128) of A and columns [n0 + r W/2, +W/2) of B, so each SM fills 16 KB + <= 16 KB of shared memory per
+// 32-deep k-block instead of 16 KB + 32 KB — the single-CTA kernel above is bound by that fill (its BN = 128 variant,
+// which needs 4/3 of the bytes per flop, runs 20-37 % slower: tools/gemm_bench.py with CG_TF32_BN128=1). The leader
+// CTA's elected thread issues every tcgen05.mma for the pair; both accumulators (128 lanes x W columns each) stay in
+// their own SM's TMEM and each CTA's epilogue warps write their 128 rows of C.
+//
+// Work is balanced by COLUMN RANGES, not whole tiles: the (m / 256) row-blocks x n columns are laid end to end and
+// every pair takes one contiguous range of U columns, cut into chunks of <= 256 columns that do not cross a row-block.
+// 1024 x 4096: 16384 columns over 74 pairs -> U = 224 (73.1 pairs busy) instead of 64 tiles of 256 on 74 pairs.
+//
+// Barriers (same offsets in both CTAs):  full[s]   leader only, 2 arrivals (one producer per CTA) + the bytes of both
+//                                        empty[s]  per CTA, released by the leader's multicast tcgen05.commit
+//                                        tfull[a]  per CTA, multicast commit after the last k-block of a chunk
+//                                        tempty[a] leader only, 8 arrivals (4 epilogue warps x 2 CTAs)
+// =====================================================================================================================
+constexpr int STAGES2 = 6;
+constexpr uint32_t A_BYTES2 = BM * BK * 4;          // 128 rows of A per CTA
+constexpr uint32_t B_BYTES2 = 128 * BK * 4;         // <= 128 columns of B per CTA
+constexpr uint32_t STAGE_BYTES2 = A_BYTES2 + B_BYTES2;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                      uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// The tile sequence of one pair (static round-robin over (row-block, column-tile)): every role of both CTAs walks
+// the same list. Consecutive pairs take consecutive column tiles of one row-block, so they share its A rows in L2.
+struct ChunkWalk {
+  int t, ntiles, stride, tiles_n, wmax;
+  __device__ __forceinline__ ChunkWalk(int pair, int npairs, int total_cols, int n, int wmax_) : wmax(wmax_) {
+    tiles_n = n / wmax_;
+    ntiles = total_cols / wmax_;
+    t = pair;
+    stride = npairs;
+  }
+  // rb: 256-row block, n0: first column, w: width (<= 256)
+  __device__ __forceinline__ bool next(int& rb, int& n0, int& w) {
+    if (t >= ntiles) return false;
+    rb = t / tiles_n;
+    n0 = (t - rb * tiles_n) * wmax;
+    w = wmax;
+    t += stride;
+    return true;
+  }
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_big,
+                          const __grid_constant__ CUtensorMap map_b_small, float* __restrict__ C, int m, int n, int k, int ldc,
+                          int epi_mode, float lr, TuneParams tp, int cols_per_pair, int wmax) {
+  // B arrives in one box of wmax / 2 columns for a full-width chunk, in 16-row (K-major) / 32-column (MN-major) boxes for
+  // the partial chunks at the ends of a range: TMA issue cost is per instruction, so the common case must be one box.
+  constexpr int SMALL = B_MN ? 32 : 16;
+  const int BIG = wmax >> 1;
+  constexpr uint32_t TMEM_COLS = 512;  // 2 accumulator stages of <= 256 columns
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE_BYTES2);
+  uint64_t* empty_bar = full_bar + STAGES2;
+  uint64_t* tfull_bar = empty_bar + STAGES2;
+  uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int total_cols = (m / 256) * n, num_kb = k / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_big) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_small) : "memory");
+    for (int s = 0; s < STAGES2; s++) {
+      mbar_init(&full_bar[s], tp.pair_peer_arrives ? 2 : 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < ACC_STAGES; s++) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    // one warp of EACH CTA of the pair performs the 2-CTA allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // barrier inits and both allocations are visible to the peer before anything is signalled
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one per CTA): its own half of the operands, signalling the LEADER's full barrier =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      ChunkWalk walk(pair, (int)(gridDim.x >> 1), total_cols, n, wmax);
+      int rb, n0, w;
+      while (walk.next(rb, n0, w)) {
+        const int m0 = rb * 256 + (int)rank * BM;
+        const int half = w >> 1, b0 = n0 + (int)rank * half;
+        const uint32_t bytes = A_BYTES2 + (uint32_t)half * BK * 4;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES2;
+          uint8_t* sb = sa + A_BYTES2;
+          const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          if (A_MN) tma2_load_3d(sa, &map_a, lbar, 0, kb * BK, m0 / 32);
+          else tma2_load_2d(sa, &map_a, lbar, kb * BK, m0);
+          int done = 0;
+          if (B_MN) {
+            for (; done + BIG <= half && !tp.pair_small_only; done += BIG) tma2_load_3d(sb + done * 128, &map_b_big, lbar, 0, kb * BK, (b0 + done) / 32);
+            for (; done < half; done += SMALL) tma2_load_3d(sb + done * 128, &map_b_small, lbar, 0, kb * BK, (b0 + done) / 32);
+          } else {
+            for (; done + BIG <= half && !tp.pair_small_only; done += BIG) tma2_load_2d(sb + done * 128, &map_b_big, lbar, kb * BK, b0 + done);
+            for (; done < half; done += SMALL) tma2_load_2d(sb + done * 128, &map_b_small, lbar, kb * BK, b0 + done);
+          }
+          // the leader accounts for the bytes of both CTAs (its single arrival + 2 x bytes complete the phase)
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * bytes);
+          else if (tp.pair_peer_arrives) mbar_arrive_cluster(lbar);
+          if (++stage == STAGES2) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
+    if (rank == 0 && lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      ChunkWalk walk(pair, (int)(gridDim.x >> 1), total_cols, n, wmax);
+      int rb, n0, w;
+      while (walk.next(rb, n0, w)) {
+        // D = F32, A = B = TF32, major bits, N >> 3, M = 256 >> 4
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                               ((uint32_t)(w >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // both epilogues have drained this accumulator stage
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(&full_bar[stage], phase);  // both CTAs' bytes have landed
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES2), sb = sa + A_BYTES2;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; kk++) {
+            const uint64_t da = A_MN ? make_smem_desc(sa + kk * tp.mn_step, tp.mn_lbo, tp.mn_sbo, tp.mn_layout)
+                                     : make_smem_desc(sa + kk * tp.k_step, tp.k_lbo, tp.k_sbo, 2);
+            const uint64_t db = B_MN ? make_smem_desc(sb + kk * tp.mn_step, tp.mn_lbo, tp.mn_sbo, tp.mn_layout)
+                                     : make_smem_desc(sb + kk * tp.k_step, tp.k_lbo, tp.k_sbo, 2);
+            tcgen05_mma_tf32_pair(tmem_d, da, db, idesc, (kb | kk) != 0);
+          }
+          tcgen05_commit_pair(&empty_bar[stage]);  // frees the slot in BOTH CTAs once these MMAs have read it
+          if (++stage == STAGES2) stage = 0, phase ^= 1;
+        }
+        tcgen05_commit_pair(&tfull_bar[acc]);  // accumulators complete -> both epilogues
+        if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue (each CTA: its own 128 rows): TMEM -> registers -> coalesced column stores =====
+    const int quad = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    ChunkWalk walk(pair, (int)(gridDim.x >> 1), total_cols, n, wmax);
+    int rb, n0, w;
+    while (walk.next(rb, n0, w)) {
+      const int m0 = rb * 256 + (int)rank * BM;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      float* crow = C + (size_t)n0 * ldc + m0 + quad * 32 + lane;
+      const int nchunks = w >> 5;
+#pragma unroll 1
+      for (int c = 0; c < nchunks; c++) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(quad * 32) << 16), v);
+        tmem_ld_wait();
+        if (c == nchunks - 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+            else mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[acc]), 0));
+          }
+        }
+        float* cp = crow + (size_t)(c * 32) * ldc;
+        if (epi_mode == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) cp[(size_t)j * ldc] = __uint_as_float(v[j]);
+        } else if (epi_mode == 1) {
+          float old[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) old[j] = cp[(size_t)j * ldc];
+#pragma unroll
+          for (int j = 0; j < 32; j++) cp[(size_t)j * ldc] = __fsub_rn(old[j], __fmul_rn(__uint_as_float(v[j]), lr));
+        } else {
+          float old[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) old[j] = cp[(size_t)j * ldc];
+#pragma unroll
+          for (int j = 0; j < 32; j++) cp[(size_t)j * ldc] = __fadd_rn(old[j], __uint_as_float(v[j]));
+        }
+      }
+      if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
+    }
+  }
+
+  // neither CTA may leave (or free TMEM) while the peer can still signal its barriers or read its shared memory
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -358,6 +628,10 @@ TuneParams tune_params() {
     env("CG_TF32_MN_LBO", t.mn_lbo), env("CG_TF32_MN_SBO", t.mn_sbo), env("CG_TF32_MN_STEP", t.mn_step);
     t.mn_chunked = 0;
     env("CG_TF32_MN_CHUNKED", t.mn_chunked), env("CG_TF32_MN_LAYOUT", t.mn_layout);
+    t.pair_peer_arrives = 0, t.pair_small_only = 0;
+    env("CG_TF32_PAIR_PEER_ARRIVES", t.pair_peer_arrives), env("CG_TF32_PAIR_SMALL_ONLY", t.pair_small_only);
+    t.debug_clock = 0;
+    env("CG_TF32_DEBUG_CLOCK", t.debug_clock);
     return t;
   }();
   return tp;
@@ -366,15 +640,16 @@ TuneParams tune_params() {
 template <int BN, bool A_MN, bool B_MN>
 void launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, float* C, int m, int n, int k, int ldc,
                     const GemmEpilogue& epi, cudaStream_t stream) {
+  constexpr int STAGES = BN == 256 ? 4 : 6;  // 192 KB of operands in flight either way
   constexpr size_t smem = (size_t)STAGES * (BM + BN) * BK * 4 + 256 + 1024;
   static bool configured = false;
   if (!configured) {
-    CG_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CG_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const int tiles = (m / BM) * (n / BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_tf32_kernel<BN, A_MN, B_MN><<<grid, NUM_THREADS, smem, stream>>>(ma, mb, C, m, n, k, ldc, epi.mode, epi.lr, tune_params());
+  gemm_tf32_kernel<BN, A_MN, B_MN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(ma, mb, C, m, n, k, ldc, epi.mode, epi.lr, tune_params());
   CG_CUDA(cudaGetLastError());
 }
 
@@ -393,7 +668,70 @@ void launch_bn(const float* A, bool ta, const float* B, bool tb, float* C, int m
   else launch_variant<BN, false, true>(ma, mb, C, m, n, k, ldc, epi, stream);
 }
 
+template <bool A_MN, bool B_MN>
+void launch_pair_variant(const CUtensorMap& ma, const CUtensorMap& mb_big, const CUtensorMap& mb_small, float* C, int m, int n,
+                         int k, int ldc, const GemmEpilogue& epi, int cols_per_pair, int wmax, int pairs, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)STAGES2 * STAGE_BYTES2 + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    CG_CUDA(cudaFuncSetAttribute(gemm_tf32_pair_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;  // the CTA pair: two SMs of one TPC
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_pair_kernel<A_MN, B_MN>, ma, mb_big, mb_small, C, m, n, k, ldc, epi.mode, epi.lr,
+                             tune_params(), cols_per_pair, wmax));
+}
+
+// Off by default: measured on B200 (tools/gemm_sweep.py) the pair kernel's main loop is marginally faster per k-block
+// (0.356 vs 0.374 us) but its fixed cost (cluster launch, two cluster barriers) is higher (9.4 vs 4.3 us), so at the
+// hot-path shapes (K = 1024 / 4096) the single-CTA kernel wins or ties. cg_set_tf32_pair(1) / CG_TF32_PAIR=1 selects it.
+int g_pair_enabled = [] {
+  const char* e = getenv("CG_TF32_PAIR");
+  return e ? atoi(e) : 0;
+}();
+bool pair_kernel_enabled() { return g_pair_enabled != 0; }
+
+bool pair_eligible(int m, int n, int k) { return pair_kernel_enabled() && m % 256 == 0 && n % 64 == 0 && k % BK == 0; }
+
+void launch_pair(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda, int ldb, int ldc,
+                 const GemmEpilogue& epi, cudaStream_t stream) {
+  const bool a_mn = !ta, b_mn = tb;
+  const int total = (m / 256) * n;
+  // widest column tile <= 256 that divides n (K-major B halves need 16-row boxes, MN-major 32-column chunks)
+  const int gran = b_mn ? 64 : 32;
+  int wmax = 256;
+  static const int forced = [] {
+    const char* e = getenv("CG_TF32_PAIR_W");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced > 0) wmax = forced;
+  while (wmax > gran && n % wmax != 0) wmax -= gran;
+  const int tiles = total / wmax;
+  const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+  const int cols = 0;
+  const CUtensorMap ma = make_operand_map(A, a_mn, m, k, lda, BM, false);
+  const CUtensorMap mb_big = make_operand_map(B, b_mn, n, k, ldb, wmax / 2, false);
+  const CUtensorMap mb_small = make_operand_map(B, b_mn, n, k, ldb, b_mn ? 32 : 16, false);
+  if (a_mn && !b_mn) launch_pair_variant<true, false>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, cols, wmax, pairs, stream);
+  else if (a_mn && b_mn) launch_pair_variant<true, true>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, cols, wmax, pairs, stream);
+  else if (!a_mn && !b_mn) launch_pair_variant<false, false>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, cols, wmax, pairs, stream);
+  else launch_pair_variant<false, true>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, cols, wmax, pairs, stream);
+}
+
 }  // namespace
+
+void gemm_tf32_set_pair(int on) { g_pair_enabled = on; }
 
 // A "true dense GEMM" (north_star item 2): whole 128-row / 128-column tiles, K in 32-float swizzle rows, and
 // enough work to fill the machine; everything else stays on the FP32 SIMT path.
@@ -409,7 +747,9 @@ void launch_gemm_tf32(const float* A, bool ta, const float* B, bool tb, float* C
                       int ldc, const GemmEpilogue& epi, cudaStream_t stream) {
   if (!gemm_tf32_aligned(A, B, lda, ldb))
     throw Error("tcgen05 product: operands must be 128-byte aligned with leading dimensions in multiples of 4");
-  if (n % 256 == 0) launch_bn<256>(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
+  if (pair_eligible(m, n, k)) return launch_pair(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
+  static const bool force128 = getenv("CG_TF32_BN128") != nullptr;
+  if (n % 256 == 0 && !force128) launch_bn<256>(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
   else launch_bn<128>(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
 }
 

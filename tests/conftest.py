@@ -38,4 +38,5 @@ def cg():
     api.set_strict_gemm_max(64)
     api.set_ew_jit_min(32768)
     api.set_io_graph(True)
+    api.set_tf32_pair(False)
     return api

@@ -185,11 +185,13 @@ def test_errors_surface_as_reference_messages(cg):
         (x + F.param("p", cg.Constant(np.ones((2, 2), np.float32)))).minimize({}, 0.1, 1)
 
 
-def test_lstm_tf32_tensor_core_path(cg, oracle):
-    """LSTM in dag mode with every product on the tcgen05 TF32 kernel (forward NN, dX NT, dW TN with the fused
+@pytest.mark.parametrize("pair", [False, True])
+def test_lstm_tf32_tensor_core_path(cg, oracle, pair):
+    """LSTM in dag mode with every product on the tcgen05 TF32 kernel (pair = True: the 2-SM cta_group::2 kernel) (forward NN, dX NT, dW TN with the fused
     SGD epilogue, dX accumulation epilogue). TF32 keeps 10 mantissa bits: tolerance 1e-3 (north_star)."""
     cg.set_mode("dag")
     cg.set_tf32(True)
+    cg.set_tf32_pair(pair)
     oracle.set_mode("dag")
     try:
         fg = readme_lstm(cg, 256, T=2, seed=21, batch=256, d_in=256, scale=1.0 / 16)
@@ -204,6 +206,7 @@ def test_lstm_tf32_tensor_core_path(cg, oracle):
             assert rel_err(lg[k], lo[k]) < 1e-3, k
     finally:
         oracle.set_mode("exact")
+        cg.set_tf32_pair(False)
 
 
 def test_host_transfers_inside_the_iteration_graph(cg, oracle):

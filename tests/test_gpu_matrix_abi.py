@@ -139,13 +139,17 @@ def test_gemm_tiled_fp32(abis, dims, t1, t2):
 
 
 @pytest.mark.parametrize("t1,t2", [(False, False), (False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("dims", [(256, 256, 128), (384, 512, 320), (1024, 768, 512)])
-def test_gemm_tcgen05_tf32(cg, abis, dims, t1, t2):
-    """tcgen05 kind::tf32 product, all four operand-major combinations. Small-integer inputs are exact in TF32
+@pytest.mark.parametrize("dims", [(256, 256, 128), (384, 512, 320), (1024, 768, 512), (256, 64, 32), (512, 832, 96),
+                                  (1024, 1408, 160), (2048, 4096, 64)])
+@pytest.mark.parametrize("pair", [False, True])
+def test_gemm_tcgen05_tf32(cg, abis, dims, t1, t2, pair):
+    """tcgen05 kind::tf32 product, all four operand-major combinations, on the single-CTA kernel and (pair = True,
+    shapes with m % 256 == 0 and n % 64 == 0) the 2-SM cta_group::2 kernel. Small-integer inputs are exact in TF32
     and their dot products exact in f32 => the result must be EXACT (catches any layout/descriptor error);
     uniform inputs are held to 1e-3 relative (TF32 keeps 10 mantissa bits; north_star tolerance)."""
     p, _ = abis
     cg.set_tf32(True)
+    cg.set_tf32_pair(pair)
     try:
         m, n, k = dims
         rng = np.random.default_rng(m + 3 * n + 7 * k)
@@ -169,3 +173,4 @@ def test_gemm_tcgen05_tf32(cg, abis, dims, t1, t2):
                 p.free(x)
     finally:
         cg.set_tf32(False)
+        cg.set_tf32_pair(False)

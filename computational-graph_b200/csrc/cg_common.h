@@ -125,6 +125,7 @@ void launch_gemm_f32(const float* A, bool ta, const float* B, bool tb, float* C,
 // eligible (caller falls back to launch_gemm_f32).
 bool gemm_tf32_eligible(int m, int n, int k, bool ta, bool tb);
 bool gemm_tf32_aligned(const float* A, const float* B, int lda, int ldb);
+void gemm_tf32_set_max_ctas(int n);  // persistent grid of the TF32 product (default: all 148 SMs)
 void gemm_tf32_set_pair(int on);  // 1: CTA-pair (cta_group::2) kernel for shapes with m % 256 == 0 and n % 64 == 0
 void launch_gemm_tf32(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda,
                       int ldb, int ldc, const GemmEpilogue& epi, cudaStream_t stream);

@@ -11,7 +11,7 @@
 #include <cstring>
 
 #include "../../include/cg_graph.h"
-#include "graph.h"
+#include "tape.h"
 
 namespace cg {
 
@@ -83,6 +83,8 @@ int cg_dp_init(int rank, int world, const unsigned char id[CG_DP_ID_BYTES]) {
     Runtime& rt = Runtime::get();
     load_nccl();
     if (g_nccl.comm) {
+      CG_CUDA(cudaStreamSynchronize(rt.stream));
+      release_all_plan_graphs();
       g_nccl.CommDestroy(g_nccl.comm);
       g_nccl.comm = nullptr;
     }
@@ -91,6 +93,10 @@ int cg_dp_init(int rank, int world, const unsigned char id[CG_DP_ID_BYTES]) {
     nccl_check(g_nccl.CommInitRank(&g_nccl.comm, world, uid, rank), "ncclCommInitRank");
     g_nccl.rank = rank;
     g_nccl.world = world;
+    // leave some SMs to the all-reduce kernels so that they overlap the products of the backward pass
+    int reserve = 16;
+    if (const char* e = getenv("CG_DP_RESERVE_SMS")) reserve = atoi(e);
+    gemm_tf32_set_max_ctas(world > 1 ? kNumSMs - reserve : kNumSMs);
     rt.dp_epoch++;
     return 0;
   } catch (const std::exception& e) {
@@ -101,9 +107,11 @@ int cg_dp_shutdown(void) {
   try {
     if (g_nccl.comm) {
       CG_CUDA(cudaStreamSynchronize(Runtime::get().stream));
+      release_all_plan_graphs();  // captured all-reduces pin the communicator: ncclCommDestroy would never return
       g_nccl.CommDestroy(g_nccl.comm);
       g_nccl.comm = nullptr;
       g_nccl.world = 1;
+      gemm_tf32_set_max_ctas(kNumSMs);
       Runtime::get().dp_epoch++;
     }
     return 0;

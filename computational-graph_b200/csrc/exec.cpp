@@ -49,7 +49,8 @@ namespace {
 struct CapNode {
   std::vector<const float*> reads, writes;
   std::function<void(cudaStream_t)> launch;
-  // >= 0: pinned to a dedicated stream (0 = copy-in, 1 = copy-out, 2 = layout kernels of the inputs); -1: any compute
+  // >= 0: pinned to a dedicated stream (0 = copy-in, 1 = copy-out, 2 = layout kernels of the inputs, 3 = collectives: every
+  // rank must issue the all-reduces of one communicator in the same order, so they share one in-order lane); -1: any compute
   // stream. A node that waits for a late transfer must not sit on a compute stream: everything captured behind it on
   // that stream would inherit the wait.
   int lane = -1;
@@ -68,6 +69,7 @@ CapNode step_node(Plan& p, size_t index, const Runtime& rt) {
     io.writes.push_back(p.vals[s.ins.dst].ptr);
     if (s.kind == Step::AVG) io.writes.push_back(rt.red_ws);  // the reduction workspace is a shared resource
   }
+  if (s.kind == Step::ALLREDUCE) io.lane = 3;
   Plan* pp = &p;
   io.launch = [pp, index](cudaStream_t st) { plan_launch_step(*pp, index, st); };
   return io;
@@ -78,7 +80,7 @@ struct Loc {
   std::vector<int> readers;
 };
 
-constexpr int kIoLanes = 3;
+constexpr int kIoLanes = 4;
 
 void capture_nodes(Plan& p, Runtime& rt, std::vector<CapNode>& nodes, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out) {
   const int nstreams = rt.graph_streams > 0 ? rt.graph_streams : 0;

@@ -121,6 +121,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// Persistent grid size. Data-parallel runs leave a few SMs to the collective kernels (dp.cpp), so that an all-reduce
+// does not wait for a whole persistent product to drain before it can start.
+int g_max_ctas = kNumSMs;
+
 struct TuneParams {
   // descriptor strides; defaults follow the canonical layouts, overridable from the environment for bring-up
   uint32_t k_lbo, k_sbo, k_step;     // K-major operand
@@ -648,7 +652,7 @@ void launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, float* C, int 
     configured = true;
   }
   const int tiles = (m / BM) * (n / BN);
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  const int grid = tiles < g_max_ctas ? tiles : g_max_ctas;
   gemm_tf32_kernel<BN, A_MN, B_MN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(ma, mb, C, m, n, k, ldc, epi.mode, epi.lr, tune_params());
   CG_CUDA(cudaGetLastError());
 }
@@ -732,6 +736,7 @@ void launch_pair(const float* A, bool ta, const float* B, bool tb, float* C, int
 }  // namespace
 
 void gemm_tf32_set_pair(int on) { g_pair_enabled = on; }
+void gemm_tf32_set_max_ctas(int n) { g_max_ctas = n < 1 ? 1 : (n > kNumSMs ? kNumSMs : n); }
 
 // A "true dense GEMM" (north_star item 2): whole 128-row / 128-column tiles, K in 32-float swizzle rows, and
 // enough work to fill the machine; everything else stays on the FP32 SIMT path.

@@ -18,13 +18,36 @@
 namespace cg {
 
 Plan::~Plan() {
+  release_graphs();
+  for (cudaEvent_t e : events) cudaEventDestroy(e);
+}
+
+void Plan::release_graphs() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (graph) cudaGraphDestroy(graph);
+  graph_exec = nullptr;
+  graph = nullptr;
   for (IoGraph& g : io) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
     if (g.graph) cudaGraphDestroy(g.graph);
+    g = IoGraph();
   }
-  for (cudaEvent_t e : events) cudaEventDestroy(e);
+}
+
+static std::vector<std::weak_ptr<Plan>>& plan_registry() {
+  static std::vector<std::weak_ptr<Plan>> r;
+  return r;
+}
+
+void release_all_plan_graphs() {
+  auto& reg = plan_registry();
+  std::vector<std::weak_ptr<Plan>> alive;
+  for (auto& w : reg)
+    if (auto p = w.lock()) {
+      p->release_graphs();
+      alive.push_back(w);
+    }
+  reg.swap(alive);
 }
 
 namespace {
@@ -679,6 +702,13 @@ void assign_memory(Plan& p) {
       int r = root_of((int)v);
       p.vals[r].last_step = std::max(p.vals[r].last_step, p.vals[v].last_step);
     }
+  // Slots that go through an all-reduce are held back for a while after their last use: recycling a gradient buffer
+  // at once would make the next weight-gradient product wait (WAR) for the previous collective and its update, and
+  // chain product -> all-reduce -> update -> product with no overlap at all.
+  std::vector<char> reduced(p.vals.size(), 0);
+  for (const Step& s : p.steps)
+    if (s.kind == Step::ALLREDUCE) reduced[root_of(s.ins.dst)] = 1;
+  const int hold = 64;  // steps (a backward LSTM step is ~25 kernels: about 20 gradient buffers in rotation)
   constexpr size_t ALIGN = 256;
   std::map<size_t, std::vector<size_t>> free_slots;  // bytes -> offsets
   std::vector<std::vector<int>> release_at(p.steps.size());
@@ -698,7 +728,9 @@ void assign_memory(Plan& p) {
         off[v] = top;
         top += bytes;
       }
-      release_at[val.last_step].push_back(v);
+      int rel = val.last_step;
+      if (reduced[v]) rel = std::min<int>(rel + hold, (int)p.steps.size() - 1);
+      release_at[rel].push_back(v);
     }
     for (int v : release_at[si]) {
       size_t bytes = (p.vals[v].sh.n() * sizeof(float) + ALIGN - 1) / ALIGN * ALIGN;
@@ -764,6 +796,7 @@ void finalize_steps(Plan& p) {
 std::shared_ptr<Plan> build_plan(Function& root, float lr) {
   Runtime& rt = Runtime::get();
   auto plan = std::make_shared<Plan>();
+  plan_registry().push_back(plan);
   Plan& p = *plan;
   p.lr = lr;
   p.mode = rt.mode;

@@ -111,9 +111,13 @@ struct Plan {
   IoGraph io[2];                    // [0] without, [1] with the D2H read of the root value
   std::vector<BufRef> io_staging;   // row-major landing buffer per matrix input
   ~Plan();
+  void release_graphs();  // destroy the captured CUDA graphs (they are re-captured on the next use)
 };
 
 std::shared_ptr<Plan> build_plan(Function& root, float lr);
+// Destroys the CUDA graphs of every live plan. NCCL keeps a communicator alive while a captured graph still holds one
+// of its collectives (ncclCommDestroy would wait forever), so cg_dp_shutdown calls this first.
+void release_all_plan_graphs();
 void plan_launch_iteration(Plan& p, cudaStream_t stream);  // enqueue the kernels of one iteration
 void plan_launch_step(Plan& p, size_t index, cudaStream_t stream);
 double plan_step_flop(const Plan& p, size_t index);

@@ -287,7 +287,10 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor" if args.product == "tf32" else "fma", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (ncu --set full,
+                     # profiles/r01_gemm_tf32_full.raw.txt): 83.9 MB + 5.0 MB; algorithmic A + B + C = 100.7 MB
+                     "traffic": 88.86e6 if args.product == "tf32" else None,
                      "kernel": f"largest product, {gcnt.value} launches/iter, {gflop.value / 1e9:.1f} GFLOP each, "
                                f"{gms.value * 1e3:.1f} us avg (CUDA events around each launch, eager pass)",
                      "peak_source": peak_note,

@@ -24,6 +24,7 @@ namespace cg {
 struct EwKernel {
   CUmodule module = nullptr;
   CUfunction fn = nullptr;
+  int blocks_per_sm = 4;  // resident CTAs of 256 threads (occupancy query): the grid is one full wave of them
 };
 
 namespace {
@@ -176,6 +177,7 @@ struct Driver {
   CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
                            void**, void**) = nullptr;
+  CUresult (*Occupancy)(int*, CUfunction, int, size_t) = nullptr;
 };
 
 Driver& driver() {
@@ -191,6 +193,7 @@ Driver& driver() {
     r.ModuleLoadData = reinterpret_cast<decltype(r.ModuleLoadData)>(get("cuModuleLoadData"));
     r.ModuleGetFunction = reinterpret_cast<decltype(r.ModuleGetFunction)>(get("cuModuleGetFunction"));
     r.LaunchKernel = reinterpret_cast<decltype(r.LaunchKernel)>(get("cuLaunchKernel"));
+    r.Occupancy = reinterpret_cast<decltype(r.Occupancy)>(get("cuOccupancyMaxActiveBlocksPerMultiprocessor"));
     return r;
   }();
   return d;
@@ -251,6 +254,8 @@ const EwKernel* ew_jit_get(const EwProgram& p) {
   CG_CUDA(cudaFree(nullptr));  // make sure the primary context is current on this thread
   drv_check(driver().ModuleLoadData(&k->module, cubin.data()), "cuModuleLoadData");
   drv_check(driver().ModuleGetFunction(&k->fn, k->module, "ew_jit"), "cuModuleGetFunction");
+  int occ = 0;
+  if (driver().Occupancy(&occ, k->fn, 256, 0) == CUDA_SUCCESS && occ > 0) k->blocks_per_sm = occ;
   g_cache[key] = k;
   return k;
 }
@@ -263,7 +268,9 @@ size_t ew_jit_cache_size() {
 void launch_ew_jit(const EwKernel* k, const EwProgram& p, cudaStream_t stream) {
   if (p.n == 0) return;
   const size_t tiles = (p.n + 1023) / 1024;
-  const size_t grid = tiles < (size_t)kNumSMs * 8 ? tiles : (size_t)kNumSMs * 8;
+  // grid-stride loop over exactly one resident wave (a ragged second wave costs up to a third of the kernel)
+  const size_t wave = (size_t)kNumSMs * (size_t)k->blocks_per_sm;
+  const size_t grid = tiles < wave ? tiles : wave;
   void* params[] = {const_cast<EwProgram*>(&p)};
   drv_check(driver().LaunchKernel(k->fn, (unsigned)grid, 1, 1, 256, 1, 1, 0, (CUstream)stream, params, nullptr), "cuLaunchKernel");
 }

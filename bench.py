@@ -109,12 +109,15 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------------
-def build_lstm(api, batch, d_in, d_hidden, steps, seed, with_inputs):
+def build_lstm(api, batch, d_in, d_hidden, steps, seed, with_inputs, shard=0):
     """(lstm(inputs) - target).sq() of src/main.rs:177-191 / src/lstm.rs:57-77 with seeded values; inputs and target
-    are `Function::input` nodes when `with_inputs` (fed per call through `args`), else constants."""
+    are `Function::input` nodes when `with_inputs` (fed per call through `args`), else constants. `shard` > 0 draws
+    a different batch shard (inputs, target) under the SAME parameters: data-parallel replicas start identical."""
     from computational_graph_b200.lstm import lstm_loss, lstm_params
     rng = np.random.default_rng(seed)
     params = lstm_params(d_in, d_hidden, batch, rng, scale=1.0 / np.sqrt(d_hidden))
+    if shard:
+        rng = np.random.default_rng(seed + 1000 * shard)
     xs = [rng.uniform(-.1, .1, (batch, d_in)).astype(np.float32) for _ in range(steps)]
     tgt = rng.uniform(-.1, .1, (batch, d_hidden)).astype(np.float32)
     if with_inputs:
@@ -214,7 +217,7 @@ def main():
     api.set_mode("dag")
     api.set_tf32(args.product == "tf32")
 
-    f, host_args = build_lstm(api, B_PER_GPU, I, H, T, SEED + rank, with_inputs=True)
+    f, host_args = build_lstm(api, B_PER_GPU, I, H, T, SEED, with_inputs=True, shard=rank)
     # pinned host buffers for the end-to-end leg
     pinned, keep = {}, []
     for k, v in host_args.items():
@@ -302,6 +305,9 @@ def main():
                                      "product": int(kind_cnt[2]), "allreduce": int(kind_cnt[3])}},
         "plan": stats,
     }
+    if world > 1:
+        line["exchange"] = ("fused all-reduce + SGD update kernel over NVLink peer memory (CUDA IPC)" if api.dp_fused()
+                            else "ncclAllReduce + elementwise update")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         its, scaled, kind, desc = cpu_sample(2, 0)
         line["cpu_baseline"] = {"value": scaled, "unit": "iterations/s", "cores": 1, "kind": kind, "sample": desc}

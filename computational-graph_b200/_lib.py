@@ -37,7 +37,8 @@ class PlanStats(C.Structure):
     """`cg_plan_stats` (include/cg_graph.h)."""
     _fields_ = [(n, C.c_ulonglong) for n in ("tape_instrs", "live_instrs", "kernels_per_iter", "ew_kernels", "gemms",
                                              "gemms_fused_sgd", "reduces", "arena_bytes")] + \
-               [("gemm_flop_per_iter", C.c_double), ("ew_bytes_per_iter", C.c_double), ("ew_specialised", C.c_ulonglong)]
+               [("gemm_flop_per_iter", C.c_double), ("ew_bytes_per_iter", C.c_double), ("ew_specialised", C.c_ulonglong),
+                ("allreduces", C.c_ulonglong), ("dp_fused_updates", C.c_ulonglong)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -63,6 +64,7 @@ class ProductApi(Api):
         lib.cg_dp_unique_id.restype, lib.cg_dp_unique_id.argtypes = C.c_int, [C.c_char_p]
         lib.cg_dp_init.restype, lib.cg_dp_init.argtypes = C.c_int, [C.c_int, C.c_int, C.c_char_p]
         lib.cg_dp_shutdown.restype = C.c_int
+        lib.cg_dp_fused.restype = C.c_int
         lib.cg_set_ew_jit_min.restype, lib.cg_set_ew_jit_min.argtypes = None, [C.c_longlong]
         lib.cg_ew_jit_selftest.restype = C.c_longlong
         lib.cg_host_alloc.restype, lib.cg_host_alloc.argtypes = C.c_void_p, [C.c_size_t]
@@ -143,6 +145,10 @@ class ProductApi(Api):
 
     def dp_shutdown(self):
         self._check(self.lib.cg_dp_shutdown())
+
+    def dp_fused(self) -> bool:
+        """True when weight gradients are exchanged by the fused peer-memory kernel rather than ncclAllReduce."""
+        return bool(self.lib.cg_dp_fused())
 
 
 def get_api() -> ProductApi:

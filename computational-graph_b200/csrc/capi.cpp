@@ -115,7 +115,10 @@ int cg_minimize_async(cg_function* f, float lr, int iters) {
   return guard_rc([&] { minimize(*F(f), {}, lr, iters, 0, nullptr, false, /*reuse_inputs=*/true); });
 }
 int cg_synchronize(void) {
-  return guard_rc([&] { CG_CUDA(cudaStreamSynchronize(Runtime::get().stream)); });
+  return guard_rc([&] {
+    CG_CUDA(cudaStreamSynchronize(Runtime::get().stream));
+    if (dp_fused_available()) dp_check_errors();
+  });
 }
 
 // ---- read-back ----------------------------------------------------------------------------------------------------
@@ -226,6 +229,8 @@ int cg_plan_stats_get(cg_function* f, float lr, cg_plan_stats* out) {
     out->gemm_flop_per_iter = s.gemm_flop_per_iter;
     out->ew_bytes_per_iter = s.ew_bytes_per_iter;
     out->ew_specialised = s.ew_specialised;
+    out->allreduces = s.allreduces;
+    out->dp_fused_updates = s.dp_fused_updates;
   });
 }
 unsigned long long cg_launch_count(void) {
@@ -454,8 +459,9 @@ extern "C" int cg_profile_iteration(cg_function* f, float lr, double kind_ms[4],
     for (size_t i = 0; i < n; i++) {
       float ms = 0.0f;
       CG_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-      kind_ms[p.steps[i].kind] += ms;
-      kind_count[p.steps[i].kind]++;
+      const int kind = p.steps[i].kind == Step::DPUPDATE ? (int)Step::ALLREDUCE : (int)p.steps[i].kind;  // the exchange step
+      kind_ms[kind] += ms;
+      kind_count[kind]++;
       if (p.steps[i].kind == Step::GEMM && plan_step_flop(p, i) == best_flop) best_ms += ms, best_cnt++;
     }
     for (auto& e : ev) cudaEventDestroy(e);

@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <utility>
+#include <vector>
 
 namespace cg {
 
@@ -138,5 +140,33 @@ void launch_gemm(const float* A, bool ta, const float* B, bool tb, float* C, int
 // Data-parallel sum-allreduce of a weight gradient over NCCL (dp.cpp). In place.
 void dp_allreduce_sum(float* buf, size_t n, cudaStream_t stream);
 bool dp_enabled();
+
+// Fused all-reduce + SGD update over NVLink peer memory (dp_kernels.cu). Buffers are "windows": allocations every
+// rank has opened through CUDA IPC, so rank r can address the same offset in every peer's copy.
+constexpr int DP_MAX_WORLD = 8;
+constexpr int DP_THREADS = 512;
+constexpr int DP_DEFAULT_CTAS = 64;  // CG_DP_CTAS overrides
+int dp_max_ctas();
+constexpr unsigned long long DP_WAIT_TIMEOUT_NS = 4000000000ull;  // 4 s: a lost rank raises an error, never hangs the GPU
+enum { DP_FLAG_A = 0, DP_FLAG_B = 16, DP_FLAG_EPOCH = 32, DP_FLAG_TICKET = 33, DP_FLAG_ERR = 34, DP_FLAG_WORDS = 64 };
+struct DpReduceArgs {
+  const float* g[DP_MAX_WORLD];  // the partial gradient in every rank (index = rank)
+  float* w[DP_MAX_WORLD];        // the weight in every rank
+  uint32_t* flags[DP_MAX_WORLD]; // every rank's flag block (DP_FLAG_WORDS words)
+  float lr;
+  size_t n;
+  int rank, world;
+};
+void launch_dp_reduce_update(const DpReduceArgs& a, cudaStream_t stream);
+// Collective (every rank, same order): makes the cudaMalloc allocations that contain these pointers addressable from
+// every rank. Returns false when peer access is not available (plans then keep ncclAllReduce + a separate update).
+bool dp_register_windows(const std::vector<const void*>& ptrs);
+void dp_forget(const void* ptr, size_t bytes);  // a device buffer is about to be freed: drop its registrations
+size_t dp_fused_min_elems();  // weights smaller than this stay on ncclAllReduce (CG_DP_FUSED_MIN)
+// Fills the peer pointers for `local` (inside a registered window); false if it is not in one.
+bool dp_peer_pointers(const void* local, void* peers[DP_MAX_WORLD]);
+bool dp_fused_available();
+void dp_fill_flags(DpReduceArgs& a);
+void dp_check_errors();  // throws if a fused exchange timed out waiting for a peer
 
 }  // namespace cg

@@ -69,7 +69,7 @@ CapNode step_node(Plan& p, size_t index, const Runtime& rt) {
     io.writes.push_back(p.vals[s.ins.dst].ptr);
     if (s.kind == Step::AVG) io.writes.push_back(rt.red_ws);  // the reduction workspace is a shared resource
   }
-  if (s.kind == Step::ALLREDUCE) io.lane = 3;
+  if (s.kind == Step::ALLREDUCE || s.kind == Step::DPUPDATE) io.lane = 3;
   Plan* pp = &p;
   io.launch = [pp, index](cudaStream_t st) { plan_launch_step(*pp, index, st); };
   return io;
@@ -371,6 +371,8 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
   }
   const double dbg_t2 = dbg ? wall() : 0;
   if (synchronize) CG_CUDA(cudaStreamSynchronize(rt.stream));
+  // a fused data-parallel exchange that lost a peer records it instead of hanging the GPU: raise it here
+  if ((synchronize || trace) && p.stats.dp_fused_updates) dp_check_errors();
   if (dbg) {
     cudaEventRecord(dbg_ev[2], rt.stream);
     cudaEventSynchronize(dbg_ev[2]);

@@ -8,7 +8,10 @@
 namespace cg {
 
 DevBuf::~DevBuf() {
-  if (owned && ptr) cudaFree(ptr);
+  if (owned && ptr) {
+    dp_forget(ptr, (n ? n : 1) * sizeof(float));  // peers may hold this buffer open (dp.cpp)
+    cudaFree(ptr);
+  }
 }
 BufRef DevBuf::alloc(size_t n) {
   auto b = std::make_shared<DevBuf>();

@@ -418,6 +418,49 @@ void fuse_gemm_sgd(Plan& p) {
   count_uses(p);
 }
 
+// Data parallel: g = allreduce(X^T.E) ; e = g * lr ; W' = W - e  ==>  one DpUpdate (dp_kernels.cu): the kernel sums the
+// per-rank partial gradients over NVLink peer memory, applies the update once per element and stores the new weight
+// into every rank's copy. The update is hoisted to the all-reduce's position (same legality rule as fuse_gemm_sgd).
+void fuse_dp_update(Plan& p) {
+  if (!dp_fused_available()) return;
+  count_uses(p);
+  std::vector<int> user(p.vals.size(), -1);
+  for (size_t k = 0; k < p.tape.size(); k++)
+    if (!p.tape[k].dead) for_each_use(p.tape[k], [&](int v) { user[v] = (int)k; });
+  for (size_t k = 0; k < p.tape.size(); k++) {
+    Instr& ar = p.tape[k];
+    if (ar.dead || ar.op != IOp::AllReduce) continue;
+    Val& gv = p.vals[ar.dst];
+    if (gv.persistent || gv.nuses != 1 || !gv.sh.m || gv.sh.n() % 4 || gv.sh.n() < dp_fused_min_elems()) continue;
+    Instr& mu = p.tape[user[ar.dst]];
+    if (mu.op != IOp::MulI || mu.a != ar.dst || p.vals[mu.dst].nuses != 1 || p.vals[mu.dst].persistent) continue;
+    const int sub_idx = user[mu.dst];
+    Instr& sb = p.tape[sub_idx];
+    if (sb.op != IOp::Sub || sb.b != mu.dst || sb.a == mu.dst) continue;
+    const Val &oldv = p.vals[sb.a], &newv = p.vals[sb.dst];
+    if (!oldv.fixed || oldv.fixed != newv.fixed || !oldv.sh.same(gv.sh)) continue;
+    bool blocked = false;
+    for (int q = (int)k + 1; q < sub_idx && !blocked; q++) {
+      const Instr& o = p.tape[q];
+      if (o.dead) continue;
+      for_each_use(o, [&](int v) {
+        if (p.vals[v].fixed == oldv.fixed) blocked = true;
+      });
+      if (p.vals[o.dst].fixed == oldv.fixed) blocked = true;
+    }
+    if (blocked) continue;
+    ar.op = IOp::DpUpdate;
+    ar.c_in = sb.a;
+    ar.imm = mu.imm;
+    p.vals[ar.dst].alias_of = -1;  // the summed gradient is never materialised
+    ar.dst = sb.dst;
+    mu.dead = true;
+    sb.dead = true;
+    p.stats.dp_fused_updates++;
+  }
+  count_uses(p);
+}
+
 // dX accumulation in dag mode:  g = E.W^T ; err' = err + g  ==>  err' = err + E.W^T in the gemm epilogue.
 void fuse_gemm_accumulate(Plan& p) {
   count_uses(p);
@@ -629,7 +672,7 @@ void build_steps(Plan& p) {
     p.stats.live_instrs++;
     if (!is_ew(i.op)) {
       Step s;
-      s.kind = i.op == IOp::Gemm ? Step::GEMM : i.op == IOp::Avg ? Step::AVG : Step::ALLREDUCE;
+      s.kind = i.op == IOp::Gemm ? Step::GEMM : i.op == IOp::Avg ? Step::AVG : i.op == IOp::DpUpdate ? Step::DPUPDATE : Step::ALLREDUCE;
       s.ins = i;
       p.steps.push_back(std::move(s));
       k++;
@@ -708,6 +751,7 @@ void assign_memory(Plan& p) {
   std::vector<char> reduced(p.vals.size(), 0);
   for (const Step& s : p.steps)
     if (s.kind == Step::ALLREDUCE) reduced[root_of(s.ins.dst)] = 1;
+    else if (s.kind == Step::DPUPDATE) reduced[root_of(s.ins.a)] = 1;
   const int hold = 64;  // steps (a backward LSTM step is ~25 kernels: about 20 gradient buffers in rotation)
   constexpr size_t ALIGN = 256;
   std::map<size_t, std::vector<size_t>> free_slots;  // bytes -> offsets
@@ -786,9 +830,40 @@ void finalize_steps(Plan& p) {
       p.stats.gemms++;
     } else if (s.kind == Step::AVG) {
       p.stats.reduces++;
+    } else if (s.kind == Step::ALLREDUCE) {
+      p.stats.allreduces++;
     }
   }
   p.stats.kernels_per_iter = p.steps.size();
+}
+
+// Data parallel: every buffer a fused exchange touches (the partial gradient in the arena, the weight leaf) is opened
+// by every peer, and the peer pointers go into the step. Collective: every rank builds the same plan at the same time.
+void bind_dp_updates(Plan& p) {
+  std::vector<const void*> ptrs;
+  for (const Step& s : p.steps)
+    if (s.kind == Step::DPUPDATE) {
+      ptrs.push_back(p.vals[s.ins.a].ptr);
+      ptrs.push_back(p.vals[s.ins.dst].ptr);
+    }
+  if (ptrs.empty()) return;
+  if (!dp_register_windows(ptrs))
+    throw Error("data parallel: the ranks could not open each other's buffers (CUDA IPC); set CG_DP_FUSED=0 to use ncclAllReduce");
+  for (Step& s : p.steps) {
+    if (s.kind != Step::DPUPDATE) continue;
+    if (p.vals[s.ins.c_in].ptr != p.vals[s.ins.dst].ptr) throw Error("internal: fused data-parallel update is not in place");
+    void *g[DP_MAX_WORLD], *w[DP_MAX_WORLD];
+    if (!dp_peer_pointers(p.vals[s.ins.a].ptr, g) || !dp_peer_pointers(p.vals[s.ins.dst].ptr, w))
+      throw Error("internal: data-parallel buffer is not registered");
+    memset(&s.dp, 0, sizeof s.dp);
+    for (int r = 0; r < DP_MAX_WORLD; r++) {
+      s.dp.g[r] = static_cast<const float*>(g[r]);
+      s.dp.w[r] = static_cast<float*>(w[r]);
+    }
+    s.dp.lr = s.ins.imm;
+    s.dp.n = p.vals[s.ins.dst].sh.n();
+    dp_fill_flags(s.dp);
+  }
 }
 
 }  // namespace
@@ -831,12 +906,14 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr) {
   dead_code_elimination(p);
   if (p.fuse) {
     fuse_gemm_sgd(p);
+    fuse_dp_update(p);
     fuse_gemm_accumulate(p);
     dead_code_elimination(p);
   }
   build_steps(p);
   assign_memory(p);
   finalize_steps(p);
+  bind_dp_updates(p);
   return plan;
 }
 
@@ -875,6 +952,7 @@ void plan_launch_step(Plan& p, size_t index, cudaStream_t stream) {
                     p.tf32 != 0, stream);
       } break;
       case Step::ALLREDUCE: dp_allreduce_sum(p.vals[s.ins.dst].ptr, p.vals[s.ins.dst].sh.n(), stream); break;
+      case Step::DPUPDATE: launch_dp_reduce_update(s.dp, stream); break;
     }
   }
 }

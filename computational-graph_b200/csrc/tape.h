@@ -29,6 +29,8 @@ enum class IOp : uint8_t {
   Avg,        // dst(scalar) = reduce_sum(a) / size(a)            (ops.rs:438-442)
   Gemm,       // dst = op(a) . op(b) [epilogue]                   (ops.rs:411-422)
   AllReduce,  // dst = sum over data-parallel ranks of a (in place)
+  DpUpdate,   // dst = c_in - (sum over ranks of a) * imm, written into every rank's copy: all-reduce + SGD update
+              // of a replicated weight as one kernel over NVLink peer memory (dp_kernels.cu)
 };
 inline bool is_ew(IOp op) { return op <= IOp::Copy; }
 
@@ -63,16 +65,17 @@ struct EwGroup {
 };
 
 struct Step {
-  enum Kind { EW, AVG, GEMM, ALLREDUCE } kind;
+  enum Kind { EW, AVG, GEMM, ALLREDUCE, DPUPDATE } kind;
   EwGroup ew;
   Instr ins;  // AVG / GEMM / ALLREDUCE
+  DpReduceArgs dp;  // DPUPDATE, filled after memory assignment (peer pointers)
   EwProgram prog;  // EW, filled after memory assignment
   const EwKernel* jit = nullptr;  // EW: the program specialised into straight-line code (large domains only)
 };
 
 struct PlanStats {
   size_t tape_instrs = 0, live_instrs = 0, ew_groups = 0, gemms = 0, gemms_fused_sgd = 0, reduces = 0;
-  size_t arena_bytes = 0, kernels_per_iter = 0, ew_specialised = 0;
+  size_t arena_bytes = 0, kernels_per_iter = 0, ew_specialised = 0, allreduces = 0, dp_fused_updates = 0;
   double gemm_flop_per_iter = 0.0, ew_bytes_per_iter = 0.0;
 };
 

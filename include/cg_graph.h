@@ -103,6 +103,8 @@ typedef struct {
   unsigned long long arena_bytes;
   double gemm_flop_per_iter, ew_bytes_per_iter;
   unsigned long long ew_specialised; /* elementwise kernels compiled to straight-line code (cg_set_ew_jit_min) */
+  unsigned long long allreduces;       /* data parallel: weight gradients summed with ncclAllReduce */
+  unsigned long long dp_fused_updates; /* data parallel: all-reduce + SGD update as one peer-memory kernel */
 } cg_plan_stats;
 int cg_plan_stats_get(cg_function *f, float learn_rate, cg_plan_stats *out); /* compiles the plan if needed */
 unsigned long long cg_launch_count(void); /* kernels launched by this library so far */
@@ -120,6 +122,9 @@ int cg_profile_iteration(cg_function *f, float learn_rate, double kind_ms[4], un
 int cg_dp_unique_id(unsigned char id[CG_DP_ID_BYTES]);                      /* rank 0: ncclGetUniqueId */
 int cg_dp_init(int rank, int world, const unsigned char id[CG_DP_ID_BYTES]); /* every rank: ncclCommInitRank */
 int cg_dp_shutdown(void);
+/* 1 when the fused all-reduce + update kernel over NVLink peer memory (CUDA IPC) is in use for weights of at least
+ * CG_DP_FUSED_MIN elements (default 2^18); 0 when the ranks fell back to ncclAllReduce (or CG_DP_FUSED=0). */
+int cg_dp_fused(void);
 int cg_set_device(int device);
 
 #ifdef __cplusplus

@@ -1,5 +1,6 @@
 """Run under torchrun with N ranks (one per GPU): every rank trains its batch-row shard of one global LSTM problem
-through the CUDA path with the NCCL sum-allreduce, and the result is compared with
+through the CUDA path with the weight-gradient exchange (--exchange fused: one peer-memory kernel per weight,
+dp_kernels.cu; --exchange nccl: ncclAllReduce + update), and the result is compared with
   (a) the full-batch run of the CPU oracle (dag mode): replicated weights on every rank, row-local parameters
       against their rows — 1e-5 for f32 products; with --tf32 only the first iteration is held to 1e-3 (TF32 rounding
       is amplified from iteration to iteration, on one GPU exactly as on several);
@@ -25,7 +26,16 @@ def main():
     ap.add_argument("--inp", type=int, default=40)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="fused: the all-reduce + SGD update kernel over NVLink peer memory (dp_kernels.cu) for every "
+                         "weight; nccl: ncclAllReduce followed by the elementwise update")
     a = ap.parse_args()
+    # read once by the library (dp.cpp), so set before it loads
+    if a.exchange == "fused":
+        os.environ["CG_DP_FUSED"] = "1"
+        os.environ["CG_DP_FUSED_MIN"] = "0"
+    else:
+        os.environ["CG_DP_FUSED"] = "0"
     import torch
     import torch.distributed as dist
     import computational_graph_b200 as pkg
@@ -56,7 +66,12 @@ def main():
     p_r, x_r, t_r = shard_lstm_problem(params, xs, tgt, rank, world)
     f = lstm_loss(api, [api.Constant(x) for x in x_r], api.Constant(t_r), p_r)
     st = api.plan_stats(f, 0.01)
-    note(f"plan built: {st['kernels_per_iter']} kernels/iter")
+    note(f"plan built: {st['kernels_per_iter']} kernels/iter, {st['dp_fused_updates']} fused exchanges, "
+         f"{st['allreduces']} ncclAllReduce")
+    if a.exchange == "fused":
+        assert api.dp_fused() and st["dp_fused_updates"] > 0 and st["allreduces"] == 0, "fused exchange not in use"
+    else:
+        assert not api.dp_fused() and st["dp_fused_updates"] == 0 and st["allreduces"] > 0, "NCCL exchange not in use"
     tr1 = np.array(f.minimize({}, 0.01, 1, trace=True))
     tr = np.concatenate([tr1, np.array(f.minimize({}, 0.01, a.iters - 1, trace=True))]) if a.iters > 1 else tr1
     note("iterations done")
@@ -97,7 +112,7 @@ def main():
     dist.all_reduce(ok[:1], op=dist.ReduceOp.MIN)
     dist.all_reduce(ok[1:], op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"dp_check world={world} tf32={a.tf32} worst_err/tol={float(ok[1]):.3e} "
+        print(f"dp_check world={world} tf32={a.tf32} exchange={a.exchange} worst_err/tol={float(ok[1]):.3e} "
               f"kernels/iter={st['kernels_per_iter']} -> {'OK' if float(ok[0]) == 1.0 else 'FAIL'}")
     dist.destroy_process_group()
     sys.exit(0 if float(ok[0]) == 1.0 else 1)

@@ -1,0 +1,142 @@
+"""Parity at BASELINE.json's FULL sizes (C2: 8192 x 8192; C4: LSTM H = I = 4096, T = 8, batch 1024), where the
+CPU oracle either needs tens of seconds (C2) or cannot finish at all (C4: 6 TFLOP per iteration). What is checked:
+
+  * C2, full size, 3 steps: directly against the oracle (reference-compiled CPU backend), tolerance 1e-5 on the
+    root value and on every leaf, and bit-exact on the one leaf whose update involves no transcendental
+    (the `abs` use site of W: d|W|/dW = sign(W), root error = 1, update = W - sign(W) * lr);
+  * C4, full size, through size-independent properties of the path:
+      - replay determinism: two runs from the same seeded state are bit-identical (the iteration is a multi-stream
+        CUDA graph: a missing dependency between two kernels shows up here as a diverging bit),
+      - product variants agree: tcgen05 TF32 products against FP32 SIMT products, 1e-3 (north_star's TF32
+        tolerance), on the root value and on every leaf after one iteration,
+      - the SGD identity W' = W - lr * X^T.E: the update of an input weight has its column space inside
+        span(X^T) (rank <= batch = 1024 < 4096), so u^T (W - W') = 0 for every u with X u = 0 — tested in float64
+        against the host copy of the step's input X, without ever recomputing E.
+Leaves are summarised on the fly (CRC of the bytes, a strided sample) so the module holds no 5 GB copies.
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+from helpers import c2_graph, leaves_dict, rel_err
+
+pytestmark = pytest.mark.gpu
+
+H = I = 4096
+T = 8
+B = 1024
+LR = 0.01
+
+
+def test_c2_full_size_three_steps_against_the_oracle(cg, oracle):
+    n = 8192
+    fg, fo = c2_graph(cg, n), c2_graph(oracle, n)
+    names = [k for k, _ in fg.leaves()]
+    assert names == ["W", "V", "W"]  # W's two use sites are separate leaves (Q1)
+    w0 = np.array(fg.leaves()[2][1])  # W at the `abs` use site, before any update
+    fg.minimize({}, LR, 3)
+    fo.minimize({}, LR, 3)
+    vg, vo = np.asarray(fg.value()), np.asarray(fo.value())
+    assert vg.shape == (n, n)
+    assert rel_err(vg, vo) < 1e-5
+    del vg, vo
+    lg, lo = leaves_dict(fg), leaves_dict(fo)
+    assert list(lg) == list(lo) and len(lg) == 3
+    for k in lg:
+        assert rel_err(lg[k], lo[k]) < 1e-5, k
+    # the abs branch: three updates W <- W - sign(W) * 0.01, no libm involved -> bit-exact (Q8: sign(+-0) = +1)
+    assert np.array_equal(lg["2:W"].view(np.int32), lo["2:W"].view(np.int32))
+    w = w0
+    for _ in range(3):
+        step = np.where(w < 0, np.float32(-1), np.float32(1)) * np.float32(LR)
+        w = (w - step).astype(np.float32)
+    assert np.array_equal(lg["2:W"].view(np.int32), w.view(np.int32))
+
+
+def _run_c4(api, tf32):
+    """One iteration of the full-size C4 graph; returns (root value, [(name, crc, sample)], Wi evidence, inputs)."""
+    from computational_graph_b200.lstm import lstm_loss, lstm_params
+    api.set_mode("dag")
+    api.set_tf32(tf32)
+    rng = np.random.default_rng(4)
+    params = lstm_params(I, H, B, rng, scale=1.0 / np.sqrt(H))
+    xs = [rng.uniform(-.1, .1, (B, I)).astype(np.float32) for _ in range(T)]
+    tgt = rng.uniform(-.1, .1, (B, H)).astype(np.float32)
+    f = lstm_loss(api, [api.Constant(x) for x in xs], api.Constant(tgt), params)
+    root = np.array(f.minimize({}, LR, 1, trace=True))
+    summary, wi_delta = [], []
+    for name, v in f.leaves():
+        v = np.ascontiguousarray(v)
+        summary.append((name, zlib.crc32(v.tobytes()), v.reshape(-1)[::997].copy()))
+        if name == "Wi" and len(wi_delta) < 2:  # (W - W') / lr for the first two Wi copies the walker lists
+            wi_delta.append((np.asarray(params["Wi"], dtype=np.float64) - v.astype(np.float64)) / LR)
+    del f
+    return root, summary, wi_delta, xs
+
+
+@pytest.fixture(scope="module")
+def c4_runs():
+    import computational_graph_b200 as pkg
+    api = pkg.get_api()
+    api.set_fix_act_grad(False)
+    api.set_fuse(True)
+    api.set_cuda_graph(True)
+    api.set_tf32_pair(False)
+    api.set_ew_jit_min(32768)
+    api.set_io_graph(True)
+    try:
+        out = {"tf32_a": _run_c4(api, True), "tf32_b": _run_c4(api, True), "f32": _run_c4(api, False)}
+    finally:
+        api.set_mode("exact")
+        api.set_tf32(False)
+    return out
+
+
+def test_c4_full_size_replay_is_bit_identical(c4_runs):
+    ra, sa, *_ = c4_runs["tf32_a"]
+    rb, sb, *_ = c4_runs["tf32_b"]
+    assert ra.shape[-2:] == (B, H) and np.all(np.isfinite(ra))
+    assert np.array_equal(ra.view(np.int32), rb.view(np.int32))
+    assert [(n, c) for n, c, _ in sa] == [(n, c) for n, c, _ in sb]
+
+
+def test_c4_full_size_tf32_and_fp32_products_agree(c4_runs):
+    rt, st, *_ = c4_runs["tf32_a"]
+    rf, sf, *_ = c4_runs["f32"]
+    assert [n for n, _, _ in st] == [n for n, _, _ in sf] and len(st) > 60
+    assert np.all(np.isfinite(rf))
+    assert rel_err(rt, rf) < 1e-3  # north_star: 1e-3 where TF32 is enabled
+    for i, ((n, _, a), (_, _, b)) in enumerate(zip(st, sf)):
+        assert rel_err(a, b) < 1e-3, (i, n)
+
+
+@pytest.mark.parametrize("variant,bound", [("f32", 1e-5), ("tf32_a", 1e-2)])
+def test_c4_full_size_weight_update_lies_in_the_span_of_its_input(c4_runs, variant, bound):
+    """optimize.rs:149-152,197-198: Wi' = Wi - lr * (X_t^T . E). Whatever E is, every column of X_t^T.E is a
+    combination of the 1024 rows of X_t, so u^T (Wi - Wi') vanishes for u orthogonal to those rows. FP32 products: the
+    residual is rounding of the subtraction only (measured ~1e-7 of the largest entry); TF32 products round X itself
+    to 10 mantissa bits first, which leaves the span by ~1e-3, hence the looser bound."""
+    _, _, wi_delta, xs = c4_runs[variant]
+    assert wi_delta, "no Wi leaf"
+    rng = np.random.default_rng(0)
+    qs = []
+    for x in xs:
+        q, _ = np.linalg.qr(x.astype(np.float64).T)  # [I, B]: orthonormal basis of span(X_t^T)
+        qs.append(q)
+    for d in wi_delta:
+        scale = float(np.max(np.abs(d)))
+        assert scale > 0.0, "this weight was not updated"
+        best, null_best = None, None
+        for q in qs:
+            u = rng.standard_normal((I, 4))
+            u -= q @ (q.T @ u)
+            u /= np.linalg.norm(u, axis=0)
+            resid = float(np.max(np.abs(u.T @ d))) / scale
+            best = resid if best is None else min(best, resid)
+        # control: a direction that is NOT orthogonal to the input sees the update
+        u = rng.standard_normal((I, 4))
+        u /= np.linalg.norm(u, axis=0)
+        control = float(np.max(np.abs(u.T @ d))) / scale
+        assert best < bound, (best, control)
+        assert control > 100 * best or control > 1e-2, (best, control)

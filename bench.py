@@ -158,10 +158,53 @@ def cpu_sample(steps, warmup):
     return its, scaled, kind, desc
 
 
+def cpu_config_lines():
+    """SURVEY §8d "CPU reference timing": the reference's CPU arithmetic (oracle/_ref, compiled unmodified from
+    src/cpu with build.rs's flags = -O0, and with -O3 -ffp-contract=off as the fair column; bit-identical results)
+    under the restated walker, one host core, on the secondary BASELINE configs C1-C3. One JSON line per config."""
+    from helpers import c2_graph, readme_lstm
+    from oracle.oracle import get_oracle
+    orc = get_oracle()
+    orc.set_mode("exact")
+    ncpu = os.cpu_count()
+
+    def timed(f, lr, iters, warm=1):
+        if warm:
+            f.minimize({}, lr, warm)
+        t0 = time.perf_counter()
+        f.minimize({}, lr, iters)
+        return (time.perf_counter() - t0) / iters
+
+    for build in ("O0", "O3"):
+        if not orc.use_ref(build):
+            print(json.dumps({"impl": "reference", "build": build, "unavailable": "oracle/_ref is not built"}))
+            continue
+        tag = {"O0": "reference src/cpu, build.rs flags (-O0)", "O3": "reference src/cpu, -O3 -ffp-contract=off"}[build]
+        x = orc.Function.scalar_param("x", 1.0)
+        s = timed((x + orc.Function.scalar(3.0)).sq(), LR, 1000, warm=10)
+        print(json.dumps({"impl": "reference", "build": tag, "cores": 1, "host_cpus": ncpu, "config": "C1 (x+3)^2 scalar",
+                          "us_per_iter": s * 1e6, "iters_per_s": 1.0 / s}))
+        n = 8192 if build == "O3" else 4096
+        s = timed(c2_graph(orc, n), LR, 2, warm=0) * (8192 / n) ** 2
+        print(json.dumps({"impl": "reference", "build": tag, "cores": 1, "host_cpus": ncpu,
+                          "config": "C2 tanh(sigmoid(W)-sq(V))+abs(W), 8192x8192",
+                          "sample": f"2 steps at {n}x{n}" + ("" if n == 8192 else ", scaled by element count to 8192x8192"),
+                          "ms_per_step": s * 1e3, "steps_per_s": 1.0 / s}))
+        for d in (5, 10, 15, 20, 25, 30):
+            iters = 200 if d <= 15 else 50
+            s = timed(readme_lstm(orc, d), LR, iters, warm=2)
+            print(json.dumps({"impl": "reference", "build": tag, "cores": 1, "host_cpus": ncpu,
+                              "config": f"C3 README LSTM T=2 d={d} ({13 * d * d} params), exact mode",
+                              "sample": f"{iters} iterations", "us_per_iter": s * 1e6, "iters_per_s": 1.0 / s}))
+    orc.use_port()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.cpu_configs:
+        return cpu_config_lines()
     steps = max(1, min(args.steps, 20))
     warm = min(args.warmup, 1)
     its, scaled, kind, desc = cpu_sample(steps, warm)
@@ -193,6 +236,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--product", default=os.environ.get("CG_BENCH_PRODUCT", "tf32"), choices=["tf32", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-configs", action="store_true",
+                    help="with --impl reference: time the reference CPU path on the secondary configs C1-C3 instead")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

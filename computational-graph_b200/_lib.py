@@ -50,7 +50,7 @@ class ProductApi(Api):
     def __init__(self, lib: C.CDLL):
         super().__init__(lib, "cg_")
         for name in ("set_tf32", "set_fix_act_grad", "set_fuse", "set_cuda_graph", "set_strict_gemm_max",
-                     "set_graph_streams", "set_io_graph", "set_tf32_pair"):
+                     "set_graph_streams", "set_io_graph", "set_tf32_pair", "set_hoist"):
             fn = self._sym(name)
             fn.restype, fn.argtypes = None, [C.c_int]
         lib.cg_launch_count.restype = C.c_ulonglong
@@ -115,6 +115,7 @@ class ProductApi(Api):
     def set_ew_jit_min(self, min_elems: int): self.lib.cg_set_ew_jit_min(int(min_elems))
     def set_tf32_pair(self, on: bool): self.lib.cg_set_tf32_pair(int(on))
     def set_io_graph(self, on: bool): self.lib.cg_set_io_graph(int(on))
+    def set_hoist(self, on: bool): self.lib.cg_set_hoist(int(on))
     def set_device(self, dev: int): self._check(self.lib.cg_set_device(int(dev)))
     def launch_count(self) -> int: return int(self.lib.cg_launch_count())
     def synchronize(self): self._check(self.lib.cg_synchronize())
@@ -123,6 +124,17 @@ class ProductApi(Api):
         st = PlanStats()
         self._check(self.lib.cg_plan_stats_get(f._h, float(learn_rate), C.byref(st)))
         return st.as_dict()
+
+    def plan_describe(self, f, learn_rate: float) -> List[str]:
+        """One line per kernel of the compiled iteration, in launch order (cg_plan_describe)."""
+        fn = self.lib.cg_plan_describe
+        fn.restype, fn.argtypes = C.c_longlong, [C.c_void_p, C.c_float, C.c_char_p, C.c_ulonglong]
+        need = fn(f._h, float(learn_rate), None, 0)
+        if need < 0:
+            self._check(-1)
+        buf = C.create_string_buffer(int(need))
+        fn(f._h, float(learn_rate), buf, need)
+        return buf.value.decode().splitlines()
 
     def time_iterations(self, f, learn_rate: float, warmup: int, reps: int) -> float:
         """ms per iteration, CUDA events on the library stream (inputs already resident in HBM)."""

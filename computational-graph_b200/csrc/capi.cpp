@@ -199,6 +199,19 @@ void cg_set_tf32_pair(int v) {
   });
 }
 void cg_set_io_graph(int v) { guard_rc([&] { Runtime::get().io_graph = v; }); }
+int cg_set_plan_only(int on) {
+  return guard_rc([&] {
+    if (Runtime::get_if_initialised()) throw Error("cg_set_plan_only must be the first call into the library");
+    set_plan_only(on != 0);
+  });
+}
+void cg_set_hoist(int v) {
+  guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    if (rt.hoist != v) rt.dp_epoch++;  // the tape order is part of a compiled plan: invalidate cached plans
+    rt.hoist = v;
+  });
+}
 void cg_set_graph_streams(int v) {
   guard_rc([&] {
     Runtime& rt = Runtime::get();
@@ -232,6 +245,19 @@ int cg_plan_stats_get(cg_function* f, float lr, cg_plan_stats* out) {
     out->allreduces = s.allreduces;
     out->dp_fused_updates = s.dp_fused_updates;
   });
+}
+long long cg_plan_describe(cg_function* f, float lr, char* buf, unsigned long long cap) {
+  long long need = -1;
+  guard_rc([&] {
+    const std::string d = plan_describe(ensure_plan(*F(f), lr));
+    need = (long long)d.size() + 1;
+    if (buf && cap) {
+      const size_t n = std::min<size_t>(d.size(), (size_t)cap - 1);
+      memcpy(buf, d.data(), n);
+      buf[n] = 0;
+    }
+  });
+  return need;
 }
 unsigned long long cg_launch_count(void) {
   unsigned long long n = 0;

@@ -136,9 +136,12 @@ char* allocation_base(const void* p) {
 
 }  // namespace
 
-bool dp_enabled() { return g_nccl.comm != nullptr && g_nccl.world > 1; }
+// plan-only mode (graph.cpp): a pretended world, so that the data-parallel tape can be inspected without GPUs
+static int g_plan_world = 1, g_plan_fused = 0;
 
-bool dp_fused_available() { return g_fused == 1; }
+bool dp_enabled() { return plan_only() ? g_plan_world > 1 : g_nccl.comm != nullptr && g_nccl.world > 1; }
+
+bool dp_fused_available() { return plan_only() ? g_plan_world > 1 && g_plan_fused : g_fused == 1; }
 
 size_t dp_fused_min_elems() {
   static const size_t v = [] {
@@ -396,6 +399,17 @@ int cg_dp_init(int rank, int world, const unsigned char id[CG_DP_ID_BYTES]) {
   }
 }
 int cg_dp_fused(void) { return dp_fused_available() ? 1 : 0; }
+int cg_dp_plan_only(int world, int fused) {
+  try {
+    if (!plan_only()) throw Error("cg_dp_plan_only is only available in plan-only mode (cg_set_plan_only)");
+    g_plan_world = world;
+    g_plan_fused = fused;
+    Runtime::get().dp_epoch++;
+    return 0;
+  } catch (const std::exception& e) {
+    return cg_dp_set_error(e.what());
+  }
+}
 int cg_dp_shutdown(void) {
   try {
     if (g_nccl.comm) {

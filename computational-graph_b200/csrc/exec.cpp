@@ -301,6 +301,10 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
     f.plan = build_plan(f, lr);
   }
   Plan& p = *f.plan;
+  if (plan_only()) {
+    if (iters > 0) throw Error("plan-only mode: minimize needs a CUDA device (this backend has no CPU path)");
+    return;  // the plan is compiled; nothing is captured or launched
+  }
   static const bool dbg = getenv("CG_DEBUG_TIMING") != nullptr;
   cudaEvent_t dbg_ev[3] = {};
   double dbg_t0 = 0;

@@ -7,8 +7,18 @@
 
 namespace cg {
 
+// Plan-only mode (cg_set_plan_only): graphs and plans are built with placeholder addresses so that the tape
+// compiler — fusion, hoisting, arena assignment, kernel counts — can be inspected and tested on a machine without a
+// GPU. Nothing is ever computed in this mode: every call that would touch the device raises.
+static bool g_plan_only = false;
+bool plan_only() { return g_plan_only; }
+void set_plan_only(bool on) { g_plan_only = on; }
+static void no_device(const char* what) {
+  throw Error(std::string("plan-only mode: ") + what + " needs a CUDA device (this backend has no CPU path)");
+}
+
 DevBuf::~DevBuf() {
-  if (owned && ptr) {
+  if (owned && ptr && !placeholder) {
     dp_forget(ptr, (n ? n : 1) * sizeof(float));  // peers may hold this buffer open (dp.cpp)
     cudaFree(ptr);
   }
@@ -17,24 +27,38 @@ BufRef DevBuf::alloc(size_t n) {
   auto b = std::make_shared<DevBuf>();
   b->n = n;
   b->owned = true;
+  if (g_plan_only) {
+    // distinct, never dereferenced, 256-byte aligned addresses from a range no allocator hands out
+    static uintptr_t next = (uintptr_t)1 << 56;
+    b->ptr = reinterpret_cast<float*>(next);
+    next += (((n ? n : 1) * sizeof(float)) + 255) / 256 * 256;
+    b->placeholder = true;
+    return b;
+  }
   CG_CUDA(cudaMalloc(&b->ptr, (n ? n : 1) * sizeof(float)));
   return b;
 }
 
+static Runtime g_rt;
 Runtime& Runtime::get() {
-  static Runtime rt;
-  if (!rt.stream) rt.init();
-  return rt;
+  if (!g_rt.stream) g_rt.init();
+  return g_rt;
 }
+bool Runtime::get_if_initialised() { return g_rt.stream != nullptr; }
 void Runtime::init() {
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0)
-    throw Error("libcg_b200: no CUDA device available — this backend has no CPU fallback");
-  CG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  CG_CUDA(cudaMalloc(&flag, 16 * sizeof(int)));  // [0] comparison flag, [4] reduce_sum result
-  CG_CUDA(cudaMalloc(&red_ws, reduce_workspace_floats() * sizeof(float)));
-  CG_CUDA(cudaMemset(red_ws, 0, reduce_workspace_floats() * sizeof(float)));
+  if (g_plan_only) {
+    stream = reinterpret_cast<cudaStream_t>((uintptr_t)1);  // placeholder: marks the runtime as initialised
+    ew_jit_min = -1;                                        // specialised kernels are loaded on a device
+  } else {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      throw Error("libcg_b200: no CUDA device available — this backend has no CPU fallback");
+    CG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CG_CUDA(cudaMalloc(&flag, 16 * sizeof(int)));  // [0] comparison flag, [4] reduce_sum result
+    CG_CUDA(cudaMalloc(&red_ws, reduce_workspace_floats() * sizeof(float)));
+    CG_CUDA(cudaMemset(red_ws, 0, reduce_workspace_floats() * sizeof(float)));
+  }
   if (const char* s = getenv("CG_MODE")) mode = (strcmp(s, "dag") == 0) ? 1 : 0;
   if (const char* s = getenv("CG_TF32")) tf32 = atoi(s);
   if (const char* s = getenv("CG_FIX_ACT_GRAD")) fix_act_grad = atoi(s);
@@ -42,10 +66,13 @@ void Runtime::init() {
   if (const char* s = getenv("CG_CUDA_GRAPH")) use_graph = atoi(s);
   if (const char* s = getenv("CG_GRAPH_STREAMS")) graph_streams = atoi(s);
   if (const char* s = getenv("CG_IO_GRAPH")) io_graph = atoi(s);
+  if (const char* s = getenv("CG_HOIST")) hoist = atoi(s);
   if (const char* s = getenv("CG_EW_JIT_MIN")) ew_jit_min = atoll(s);
+  if (g_plan_only) ew_jit_min = -1;
 }
 
 static void fill_device(float* ptr, size_t n, float v) {
+  if (g_plan_only) return;
   Runtime& rt = Runtime::get();
   EwProgram p{};
   p.n = n;
@@ -77,12 +104,15 @@ Function* make_scalar_leaf(Kind kind, const char* name, float x) {
   v.uniform = true;
   v.uval = x;
   v.buf = DevBuf::alloc(1);
-  CG_CUDA(cudaMemcpyAsync(v.buf->ptr, &x, sizeof(float), cudaMemcpyHostToDevice, rt.stream));
-  CG_CUDA(cudaStreamSynchronize(rt.stream));
+  if (!g_plan_only) {
+    CG_CUDA(cudaMemcpyAsync(v.buf->ptr, &x, sizeof(float), cudaMemcpyHostToDevice, rt.stream));
+    CG_CUDA(cudaStreamSynchronize(rt.stream));
+  }
   return new_leaf(kind, name, std::move(v));
 }
 
 void value_upload_rowmajor(Value& v, const float* src, bool sync) {
+  if (g_plan_only) return;
   // Matrix::new -> set_array(values, transpose = true) (matrix.rs:59-66, cpu/matrix.cpp:26-36)
   Runtime& rt = Runtime::get();
   const size_t n = v.size();
@@ -129,6 +159,7 @@ Function* make_fill_leaf(Kind kind, const char* name, unsigned h, unsigned w, fl
   v.uval = x;
   v.buf = DevBuf::alloc((size_t)h * w);
   fill_device(v.buf->ptr, (size_t)h * w, x);
+  if (g_plan_only) return new_leaf(kind, name, std::move(v));
   rt.launches++;
   CG_CUDA(cudaStreamSynchronize(rt.stream));
   return new_leaf(kind, name, std::move(v));
@@ -142,7 +173,7 @@ Function* make_input(const char* name, bool is_matrix, unsigned h, unsigned w) {
   v.w = is_matrix ? w : 0;
   v.defined = false;
   v.buf = DevBuf::alloc(v.size());
-  CG_CUDA(cudaMemset(v.buf->ptr, 0, v.size() * sizeof(float)));
+  if (!g_plan_only) CG_CUDA(cudaMemset(v.buf->ptr, 0, v.size() * sizeof(float)));
   return new_leaf(Kind::Input, name, std::move(v));
 }
 
@@ -152,8 +183,10 @@ static Value clone_value(const Value& v) {
   if (v.buf) {
     Runtime& rt = Runtime::get();
     c.buf = DevBuf::alloc(v.size());
-    CG_CUDA(cudaMemcpyAsync(c.buf->ptr, v.buf->ptr, v.size() * sizeof(float), cudaMemcpyDeviceToDevice, rt.stream));
-    CG_CUDA(cudaStreamSynchronize(rt.stream));
+    if (!g_plan_only) {
+      CG_CUDA(cudaMemcpyAsync(c.buf->ptr, v.buf->ptr, v.size() * sizeof(float), cudaMemcpyDeviceToDevice, rt.stream));
+      CG_CUDA(cudaStreamSynchronize(rt.stream));
+    }
   }
   return c;
 }
@@ -179,6 +212,7 @@ Function* clone_function(const Function& f) {
 
 // ---- value predicates ------------------------------------------------------------------------------------
 static bool device_cmp(bool less, const Value& v, float x) {
+  if (g_plan_only) no_device("comparing a computed value");
   Runtime& rt = Runtime::get();
   if (!v.buf) throw Error("value has not been evaluated yet");
   if (less) launch_all_less_than(v.buf->ptr, v.size(), x, rt.flag, rt.stream);
@@ -200,6 +234,7 @@ bool value_all_less_than(const Value& v, float x) {
   return device_cmp(true, v, x);
 }
 void value_download(const Value& v, float* dst) {
+  if (g_plan_only) no_device("reading a value back");
   Runtime& rt = Runtime::get();
   if (!v.buf) throw Error("value has not been evaluated yet");
   CG_CUDA(cudaMemcpyAsync(dst, v.buf->ptr, v.size() * sizeof(float), cudaMemcpyDeviceToHost, rt.stream));

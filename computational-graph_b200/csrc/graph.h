@@ -21,6 +21,7 @@ struct DevBuf {
   size_t n = 0;
   std::shared_ptr<void> keepalive;  // arena that owns `ptr`, when not owned here
   bool owned = false;
+  bool placeholder = false;  // plan-only mode: an address that is never dereferenced
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -66,6 +67,9 @@ struct Expr {
 
 inline bool is_leaf(Kind k) { return k == Kind::Constant || k == Kind::Input || k == Kind::Param; }
 
+bool plan_only();
+void set_plan_only(bool on);
+
 // ---- global runtime state -----------------------------------------------------------------------
 struct Runtime {
   cudaStream_t stream = nullptr;
@@ -76,6 +80,7 @@ struct Runtime {
   int use_graph = 1;     // capture each iteration as a CUDA graph
   int graph_streams = 4; // side streams used when an iteration is captured as a DAG (0 = single stream)
   long long ew_jit_min = 32768;  // elementwise programs over >= this many elements are specialised (ew_jit.cpp); < 0: never
+  int hoist = 1;         // dag mode: move loss-independent backward work next to the forward ops it depends on (plan.cpp)
   int io_graph = 1;      // put the H2D / D2H transfers of a `minimize(&args, lr, 1)` call inside the iteration graph
   std::vector<cudaStream_t> side_streams;
   int dp_epoch = 0;      // bumped whenever the data-parallel configuration changes (invalidates plans)
@@ -85,6 +90,7 @@ struct Runtime {
   float* red_ws = nullptr;
   BufRef staging;        // grow-only device staging buffer for row-major uploads (never freed in a loop)
   static Runtime& get();
+  static bool get_if_initialised();
   void init();
 };
 

@@ -491,6 +491,74 @@ void fuse_gemm_accumulate(Plan& p) {
   count_uses(p);
 }
 
+// Hoisting. The reference's backward pass hands the child of a Sigmoid / Tanh only the local derivative (Q3,
+// optimize.rs:168-179), so most of "backward" — every gate's derivative, the weight-gradient products X^T.ph and
+// their SGD updates — depends on forward values alone, not on the loss. This pass moves every backward instruction
+// to just behind the last forward instruction it (transitively) depends on; the loss-carrying chain stays where it
+// was. Pure dataflow reordering: every instruction computes the same bits. What it buys: derivative ops land next
+// to the forward ops of the same shape (one elementwise kernel instead of two, one HBM pass less), activations die
+// early (smaller arena), and under data parallelism the weight exchanges are spread over the whole iteration
+// instead of queueing up behind the forward pass, where the wire then sits idle.
+// Dependencies are RAW / WAR / WAW on memory identity: SSA value, or the leaf buffer its versions share, or the
+// value an in-place result aliases.
+void hoist_backward(Plan& p, size_t n_forward) {
+  const size_t N = p.tape.size();
+  auto mem = [&](int v) -> long long {
+    while (p.vals[v].alias_of >= 0) v = p.vals[v].alias_of;
+    return p.vals[v].fixed ? (long long)(intptr_t)p.vals[v].fixed : -(long long)(v + 1);
+  };
+  struct Loc {
+    int last_writer = -1;
+    std::vector<int> readers;
+  };
+  std::unordered_map<long long, Loc> loc;
+  std::vector<long long> key(N, 0);
+  std::vector<std::vector<int>> deps(N);
+  std::vector<int> live;
+  for (size_t i = 0; i < N; i++) {
+    const Instr& in = p.tape[i];
+    if (in.dead) continue;
+    live.push_back((int)i);
+    auto dep = [&](int d) {
+      if (d >= 0 && d != (int)i) deps[i].push_back(d);
+    };
+    std::vector<long long> reads;
+    for_each_use(in, [&](int v) { reads.push_back(mem(v)); });
+    const long long w = mem(in.dst);
+    for (long long r : reads) dep(loc[r].last_writer);
+    {
+      Loc& l = loc[w];
+      dep(l.last_writer);
+      for (int rd : l.readers) dep(rd);
+    }
+    if (i < n_forward) {
+      key[i] = (long long)i;  // the forward pass is the anchor sequence
+    } else {
+      key[i] = (long long)n_forward - 1;  // no dependency at all (the root error, a Fill): start of backward
+      bool first = true;
+      for (int d : deps[i]) {
+        key[i] = first ? key[d] : std::max(key[i], key[d]);
+        first = false;
+      }
+    }
+    for (long long r : reads) loc[r].readers.push_back((int)i);
+    Loc& l = loc[w];
+    l.last_writer = (int)i;
+    l.readers.clear();
+  }
+  std::stable_sort(live.begin(), live.end(), [&](int a, int b) { return key[a] < key[b]; });
+  // the new order must be a topological order of the same dependencies
+  std::vector<int> pos(N, -1);
+  for (size_t k = 0; k < live.size(); k++) pos[live[k]] = (int)k;
+  for (int i : live)
+    for (int d : deps[i])
+      if (pos[d] < 0 || pos[d] >= pos[i]) throw Error("internal: hoisting broke a dependency");
+  std::vector<Instr> out;
+  out.reserve(live.size());
+  for (int i : live) out.push_back(p.tape[i]);
+  p.tape.swap(out);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Elementwise fusion: compile tape[s, e) into one register-bytecode program, or fail.
 // ------------------------------------------------------------------------------------------------------
@@ -846,7 +914,7 @@ void bind_dp_updates(Plan& p) {
       ptrs.push_back(p.vals[s.ins.a].ptr);
       ptrs.push_back(p.vals[s.ins.dst].ptr);
     }
-  if (ptrs.empty()) return;
+  if (ptrs.empty() || plan_only()) return;
   if (!dp_register_windows(ptrs))
     throw Error("data parallel: the ranks could not open each other's buffers (CUDA IPC); set CG_DP_FUSED=0 to use ncclAllReduce");
   for (Step& s : p.steps) {
@@ -880,6 +948,7 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr) {
   p.fuse = rt.fuse;
   p.dp_epoch = rt.dp_epoch;
   p.ew_jit_min = rt.ew_jit_min;
+  p.hoist = rt.hoist;
 
   Builder b(p, lr, rt.fix_act_grad);
   b.forward(root);
@@ -897,6 +966,7 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr) {
     p.vals[root_val].persistent = true;
     p.root_ptr = root.value.buf->ptr;
   }
+  const size_t n_forward = p.tape.size();
   // optimize.rs:69 — `let mut error = self.value_mut().copy_and_fill(1.)`
   int error = b.emit(IOp::Fill, rsh, -1, -1, 1.0f);
   if (p.mode == 0) b.backprop_tree(root, error);
@@ -910,11 +980,35 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr) {
     fuse_gemm_accumulate(p);
     dead_code_elimination(p);
   }
+  if (p.hoist && p.mode == 1) hoist_backward(p, n_forward);
   build_steps(p);
   assign_memory(p);
   finalize_steps(p);
   bind_dp_updates(p);
   return plan;
+}
+
+std::string plan_describe(const Plan& p) {
+  std::string out;
+  char line[256];
+  for (size_t i = 0; i < p.steps.size(); i++) {
+    const Step& s = p.steps[i];
+    switch (s.kind) {
+      case Step::EW:
+        snprintf(line, sizeof line, "%zu EW n=%zu in=%zu out=%zu ins=%zu\n", i, s.ew.n, s.ew.in.size(), s.ew.out.size(), s.ew.code.size());
+        break;
+      case Step::AVG: snprintf(line, sizeof line, "%zu AVG n=%zu\n", i, p.vals[s.ins.a].sh.n()); break;
+      case Step::GEMM: {
+        const Shape &as = p.vals[s.ins.a].sh, &cs = p.vals[s.ins.dst].sh;
+        snprintf(line, sizeof line, "%zu GEMM m=%u n=%u k=%u ta=%d tb=%d epi=%d\n", i, cs.h, cs.w, s.ins.ta ? as.h : as.w, (int)s.ins.ta,
+                 (int)s.ins.tb, s.ins.epi);
+      } break;
+      case Step::ALLREDUCE: snprintf(line, sizeof line, "%zu ALLREDUCE n=%zu\n", i, p.vals[s.ins.dst].sh.n()); break;
+      case Step::DPUPDATE: snprintf(line, sizeof line, "%zu DPUPDATE n=%zu\n", i, p.vals[s.ins.dst].sh.n()); break;
+    }
+    out += line;
+  }
+  return out;
 }
 
 double plan_step_flop(const Plan& p, size_t i) {

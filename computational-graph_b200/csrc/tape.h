@@ -101,7 +101,7 @@ struct Plan {
   BufRef arena;
   PlanStats stats;
   float lr = 0.0f;
-  int mode = 0, tf32 = 0, fix_act_grad = 0, fuse = 1, dp_epoch = 0;
+  int mode = 0, tf32 = 0, fix_act_grad = 0, fuse = 1, dp_epoch = 0, hoist = 0;
   long long ew_jit_min = -1;
   bool root_is_leaf = false;
   float* root_ptr = nullptr;
@@ -124,5 +124,6 @@ void release_all_plan_graphs();
 void plan_launch_iteration(Plan& p, cudaStream_t stream);  // enqueue the kernels of one iteration
 void plan_launch_step(Plan& p, size_t index, cudaStream_t stream);
 double plan_step_flop(const Plan& p, size_t index);
+std::string plan_describe(const Plan& p);  // one line per kernel of the iteration, in launch order
 
 }  // namespace cg

@@ -96,6 +96,10 @@ int cg_ew_jit_available(void);
 long long cg_ew_jit_selftest(void);   /* compiles a program using every opcode; cubin bytes or -1 (no GPU needed) */
 void cg_set_tf32_pair(int on);        /* 1: 2-SM (cta_group::2) TF32 product kernel where the shape allows; default 0 */
 void cg_set_io_graph(int on);         /* 0: never put host transfers inside the iteration graph */
+/* dag mode. 1 (default): backward work that does not depend on the loss (Q3: a Sigmoid / Tanh hands its child the local
+ * derivative only, src/optimize.rs:168-179 — every gate derivative, weight-gradient product and weight update of the
+ * LSTM) is scheduled right behind the forward op it depends on. Same arithmetic, same bits; 0 keeps the walk order. */
+void cg_set_hoist(int on);
 
 /* ---- introspection -------------------------------------------------------------------------------- */
 typedef struct {
@@ -107,6 +111,13 @@ typedef struct {
   unsigned long long dp_fused_updates; /* data parallel: all-reduce + SGD update as one peer-memory kernel */
 } cg_plan_stats;
 int cg_plan_stats_get(cg_function *f, float learn_rate, cg_plan_stats *out); /* compiles the plan if needed */
+/* One text line per kernel of the compiled iteration, in launch order ("<i> GEMM m= n= k= ta= tb= epi=", "<i> EW n= in= out=
+ * ins=", "<i> AVG", "<i> ALLREDUCE", "<i> DPUPDATE"). Returns the bytes needed (incl. NUL) or -1; buf may be NULL. */
+long long cg_plan_describe(cg_function *f, float learn_rate, char *buf, unsigned long long cap);
+/* Plan-only mode, for machines without a GPU: graphs and plans are built over placeholder addresses so that the tape
+ * compiler can be inspected (cg_plan_stats_get, cg_plan_describe); every call that would compute raises. Must be the
+ * first call into the library. */
+int cg_set_plan_only(int on);
 unsigned long long cg_launch_count(void); /* kernels launched by this library so far */
 const char *cg_last_error(void);
 /* Times `reps` replays of f's iteration with CUDA events on the library stream; returns ms per iteration. */
@@ -122,6 +133,9 @@ int cg_profile_iteration(cg_function *f, float learn_rate, double kind_ms[4], un
 int cg_dp_unique_id(unsigned char id[CG_DP_ID_BYTES]);                      /* rank 0: ncclGetUniqueId */
 int cg_dp_init(int rank, int world, const unsigned char id[CG_DP_ID_BYTES]); /* every rank: ncclCommInitRank */
 int cg_dp_shutdown(void);
+/* Plan-only mode: pretend to be one of `world` ranks (fused: with the peer-memory exchange available) so that the
+ * data-parallel tape can be inspected on a machine without GPUs. */
+int cg_dp_plan_only(int world, int fused);
 /* 1 when the fused all-reduce + update kernel over NVLink peer memory (CUDA IPC) is in use for weights of at least
  * CG_DP_FUSED_MIN elements (default 2^18); 0 when the ranks fell back to ncclAllReduce (or CG_DP_FUSED=0). */
 int cg_dp_fused(void);

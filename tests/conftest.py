@@ -39,4 +39,5 @@ def cg():
     api.set_ew_jit_min(32768)
     api.set_io_graph(True)
     api.set_tf32_pair(False)
+    api.set_hoist(True)
     return api

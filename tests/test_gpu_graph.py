@@ -133,6 +133,25 @@ def test_dag_equals_exact_without_shared_nodes(cg):
         assert np.array_equal(res[0][1][k].view(np.int32), res[1][1][k].view(np.int32)), k
 
 
+@pytest.mark.parametrize("tf32,shape", [(False, (3, 12, 9, 8)), (False, (2, 80, 72, 96)), (True, (2, 256, 256, 256))])
+def test_hoisting_is_bit_identical(cg, tf32, shape):
+    """cg_set_hoist only reorders the tape along its data dependencies (plan.cpp hoist_backward): the root values of
+    every iteration and every leaf must come out bit for bit the same with and without it."""
+    T, batch, d_in, d = shape
+    cg.set_mode("dag")
+    cg.set_tf32(tf32)
+    res = []
+    for hoist in (False, True):
+        cg.set_hoist(hoist)
+        f = readme_lstm(cg, d, T=T, seed=77, batch=batch, d_in=d_in, scale=1.0 / np.sqrt(d))
+        tr = f.minimize({}, 0.01, 4, trace=True)
+        res.append((np.asarray(tr), leaves_dict(f), cg.plan_describe(f, 0.01)))
+    assert res[0][2] != res[1][2]  # the kernel order did change
+    assert np.array_equal(res[0][0].view(np.int32), res[1][0].view(np.int32))
+    for k in res[0][1]:
+        assert np.array_equal(res[0][1][k].view(np.int32), res[1][1][k].view(np.int32)), k
+
+
 def test_medium_lstm_tiled_gemm(cg, oracle):
     """Products above the strict-kernel limit take the tiled FP32 SIMT kernel (FMA accumulation): 1e-5."""
     cg.set_mode("dag")

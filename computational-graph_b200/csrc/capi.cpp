@@ -205,6 +205,13 @@ int cg_set_plan_only(int on) {
     set_plan_only(on != 0);
   });
 }
+void cg_set_vm_max_dim(int v) {
+  guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    if (rt.vm_max_dim != v) rt.dp_epoch++;  // the executor choice is part of a compiled plan
+    rt.vm_max_dim = v;
+  });
+}
 void cg_set_hoist(int v) {
   guard_rc([&] {
     Runtime& rt = Runtime::get();
@@ -244,6 +251,7 @@ int cg_plan_stats_get(cg_function* f, float lr, cg_plan_stats* out) {
     out->ew_specialised = s.ew_specialised;
     out->allreduces = s.allreduces;
     out->dp_fused_updates = s.dp_fused_updates;
+    out->vm_resident = s.vm_resident;
   });
 }
 long long cg_plan_describe(cg_function* f, float lr, char* buf, unsigned long long cap) {

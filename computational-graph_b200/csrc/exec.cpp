@@ -315,7 +315,8 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
     cudaEventRecord(dbg_ev[0], rt.stream);
   }
   // One iteration whose host transfers ride inside the graph (pinned buffers only); otherwise: upload, then loop.
-  const bool io = !reuse_inputs && iters >= 1 && (iters == 1 || !trace) && io_graph_eligible(p, rt, args, trace);
+  const bool vm = p.vm_steps != nullptr;
+  const bool io = !vm && !reuse_inputs && iters >= 1 && (iters == 1 || !trace) && io_graph_eligible(p, rt, args, trace);
   if (!reuse_inputs && !io) upload_inputs(p, args);
   if (dbg) cudaEventRecord(dbg_ev[1], rt.stream);
   const double dbg_t1 = dbg ? wall() : 0;
@@ -323,6 +324,28 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
   f.value.summary_valid = false;
   f.value.defined = true;
 
+  if (vm) {
+    // Resident tape executor: one kernel runs every iteration up to the next print (vm_kernel.cu).
+    float* trace_dev = nullptr;
+    if (trace && iters > 0) CG_CUDA(cudaMalloc(&trace_dev, (size_t)iters * p.root_n * sizeof(float)));
+    int done = 0;
+    while (done < iters) {
+      int chunk = iters - done;
+      if (print_freq > 0) chunk = std::min(chunk, print_freq - done % print_freq);
+      launch_tape_vm(p.vm_steps, p.vm_progs, p.vm_nsteps, chunk, p.root_ptr, p.root_n, p.root_is_leaf,
+                     trace_dev ? trace_dev + (size_t)done * p.root_n : nullptr, rt.stream);
+      rt.launches++;
+      done += chunk;
+      if (print_freq > 0 && done % print_freq == 0) print_value(f.value);
+    }
+    if (trace_dev) {
+      CG_CUDA(cudaMemcpyAsync(trace, trace_dev, (size_t)iters * p.root_n * sizeof(float), cudaMemcpyDeviceToHost, rt.stream));
+      CG_CUDA(cudaStreamSynchronize(rt.stream));
+      CG_CUDA(cudaFree(trace_dev));
+    }
+    if (synchronize) CG_CUDA(cudaStreamSynchronize(rt.stream));
+    return;
+  }
   if (rt.use_graph && !p.graph_exec && !p.steps.empty() && rt.graph_streams > 0) {
     capture_dag(p, rt);
   } else if (rt.use_graph && !p.graph_exec && !p.steps.empty()) {

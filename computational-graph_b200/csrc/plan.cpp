@@ -18,6 +18,8 @@
 namespace cg {
 
 Plan::~Plan() {
+  if (vm_steps) cudaFree(vm_steps);
+  if (vm_progs) cudaFree(vm_progs);
   release_graphs();
   for (cudaEvent_t e : events) cudaEventDestroy(e);
 }
@@ -936,6 +938,8 @@ void bind_dp_updates(Plan& p) {
 
 }  // namespace
 
+void build_vm(Plan& p);
+
 std::shared_ptr<Plan> build_plan(Function& root, float lr) {
   Runtime& rt = Runtime::get();
   auto plan = std::make_shared<Plan>();
@@ -985,7 +989,58 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr) {
   assign_memory(p);
   finalize_steps(p);
   bind_dp_updates(p);
+  build_vm(p);
   return plan;
+}
+
+// Latency-bound plans (every matrix a few hundred elements: BASELINE config 3) run on the resident tape executor:
+// the whole step list goes to device memory and one CTA walks it, iteration loop included (vm_kernel.cu).
+void build_vm(Plan& p) {
+  Runtime& rt = Runtime::get();
+  if (rt.vm_max_dim <= 0 || !rt.use_graph || p.steps.empty() || p.steps.size() > 8192) return;
+  const int max_dim = std::min(rt.vm_max_dim, rt.strict_gemm_max);  // products must be the strict kernel's on both executors
+  const size_t max_elems = (size_t)rt.vm_max_dim * rt.vm_max_dim;
+  std::vector<VmStep> steps;
+  std::vector<EwProgram> progs;
+  for (const Step& s : p.steps) {
+    VmStep v;
+    memset(&v, 0, sizeof v);
+    if (s.kind == Step::EW) {
+      if (s.prog.n > max_elems) return;
+      v.kind = VmStep::EW;
+      v.prog = (int)progs.size();
+      progs.push_back(s.prog);
+    } else if (s.kind == Step::AVG) {
+      const Val& a = p.vals[s.ins.a];
+      if (a.sh.n() > kStrictReduceMax || a.sh.n() > max_elems) return;
+      v.kind = VmStep::AVG;
+      v.n = (int)a.sh.n();
+      v.a = a.ptr;
+      v.c = p.vals[s.ins.dst].ptr;
+    } else if (s.kind == Step::GEMM) {
+      const Val &a = p.vals[s.ins.a], &b = p.vals[s.ins.b], &c = p.vals[s.ins.dst];
+      v.kind = VmStep::GEMM;
+      v.m = (int)c.sh.h, v.n = (int)c.sh.w, v.k = (int)(s.ins.ta ? a.sh.h : a.sh.w);
+      if (std::max(v.m, std::max(v.n, v.k)) > max_dim) return;
+      if (s.ins.epi && p.vals[s.ins.c_in].ptr != c.ptr) throw Error("internal: gemm epilogue operand is not in place");
+      v.lda = (int)a.sh.h, v.ldb = (int)b.sh.h, v.ldc = (int)c.sh.h;
+      v.ta = s.ins.ta, v.tb = s.ins.tb, v.epi = s.ins.epi;
+      v.lr = s.ins.imm;
+      v.a = a.ptr, v.b = b.ptr, v.c = c.ptr;
+    } else {
+      return;  // data-parallel exchanges are not for one CTA
+    }
+    steps.push_back(v);
+  }
+  p.stats.vm_resident = 1;
+  if (plan_only()) return;
+  p.vm_nsteps = (int)steps.size();
+  CG_CUDA(cudaMalloc(&p.vm_steps, steps.size() * sizeof(VmStep)));
+  CG_CUDA(cudaMemcpy(p.vm_steps, steps.data(), steps.size() * sizeof(VmStep), cudaMemcpyHostToDevice));
+  if (!progs.empty()) {
+    CG_CUDA(cudaMalloc(&p.vm_progs, progs.size() * sizeof(EwProgram)));
+    CG_CUDA(cudaMemcpy(p.vm_progs, progs.data(), progs.size() * sizeof(EwProgram), cudaMemcpyHostToDevice));
+  }
 }
 
 std::string plan_describe(const Plan& p) {

@@ -73,9 +73,24 @@ struct Step {
   const EwKernel* jit = nullptr;  // EW: the program specialised into straight-line code (large domains only)
 };
 
+// One step of the resident tape executor (vm_kernel.cu), in device memory.
+struct VmStep {
+  enum { EW = 0, AVG = 1, GEMM = 2 };
+  int kind;
+  int prog;                      // EW: index into the program array
+  int m, n, k, lda, ldb, ldc;    // GEMM: C(m x n) = op(A) . op(B); AVG: n = element count
+  int ta, tb, epi;
+  float lr;
+  const float* a;                // GEMM: A; AVG: source
+  const float* b;
+  float* c;                      // GEMM: C; AVG: the 1-element destination
+};
+void launch_tape_vm(const VmStep* steps, const EwProgram* progs, int nsteps, int iters, const float* root, size_t root_n,
+                    bool root_is_leaf, float* trace, cudaStream_t stream);
+
 struct PlanStats {
   size_t tape_instrs = 0, live_instrs = 0, ew_groups = 0, gemms = 0, gemms_fused_sgd = 0, reduces = 0;
-  size_t arena_bytes = 0, kernels_per_iter = 0, ew_specialised = 0, allreduces = 0, dp_fused_updates = 0;
+  size_t arena_bytes = 0, kernels_per_iter = 0, ew_specialised = 0, allreduces = 0, dp_fused_updates = 0, vm_resident = 0;
   double gemm_flop_per_iter = 0.0, ew_bytes_per_iter = 0.0;
 };
 
@@ -113,6 +128,10 @@ struct Plan {
   std::vector<cudaEvent_t> events;  // one per captured node (+1 fork event) for the multi-stream capture
   IoGraph io[2];                    // [0] without, [1] with the D2H read of the root value
   std::vector<BufRef> io_staging;   // row-major landing buffer per matrix input
+  // resident tape executor (vm_kernel.cu): the steps and programs in device memory, when the plan is small enough
+  VmStep* vm_steps = nullptr;
+  EwProgram* vm_progs = nullptr;
+  int vm_nsteps = 0;
   ~Plan();
   void release_graphs();  // destroy the captured CUDA graphs (they are re-captured on the next use)
 };

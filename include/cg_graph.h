@@ -100,6 +100,10 @@ void cg_set_io_graph(int on);         /* 0: never put host transfers inside the 
  * derivative only, src/optimize.rs:168-179 — every gate derivative, weight-gradient product and weight update of the
  * LSTM) is scheduled right behind the forward op it depends on. Same arithmetic, same bits; 0 keeps the walk order. */
 void cg_set_hoist(int on);
+/* Latency-bound plans — every elementwise domain <= dim*dim elements and every product dimension <= min(dim, the strict
+ * limit) — are executed by ONE resident CTA that walks the whole tape, iteration loop included, instead of one CUDA-graph
+ * node per step (vm_kernel.cu; same arithmetic, same bits). Default 48 (covers the README LSTM sweep, d <= 30); 0: never. */
+void cg_set_vm_max_dim(int dim);
 
 /* ---- introspection -------------------------------------------------------------------------------- */
 typedef struct {
@@ -109,6 +113,7 @@ typedef struct {
   unsigned long long ew_specialised; /* elementwise kernels compiled to straight-line code (cg_set_ew_jit_min) */
   unsigned long long allreduces;       /* data parallel: weight gradients summed with ncclAllReduce */
   unsigned long long dp_fused_updates; /* data parallel: all-reduce + SGD update as one peer-memory kernel */
+  unsigned long long vm_resident;      /* 1: the plan runs on the resident tape executor (cg_set_vm_max_dim) */
 } cg_plan_stats;
 int cg_plan_stats_get(cg_function *f, float learn_rate, cg_plan_stats *out); /* compiles the plan if needed */
 /* One text line per kernel of the compiled iteration, in launch order ("<i> GEMM m= n= k= ta= tb= epi=", "<i> EW n= in= out=

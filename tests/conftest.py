@@ -40,4 +40,5 @@ def cg():
     api.set_io_graph(True)
     api.set_tf32_pair(False)
     api.set_hoist(True)
+    api.set_vm_max_dim(48)
     return api

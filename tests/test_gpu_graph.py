@@ -152,6 +152,53 @@ def test_hoisting_is_bit_identical(cg, tf32, shape):
         assert np.array_equal(res[0][1][k].view(np.int32), res[1][1][k].view(np.int32)), k
 
 
+@pytest.mark.parametrize("case", ["c3_exact_d5", "c3_exact_d30", "c3_dag_d30", "broadcast_avg", "inputs"])
+def test_resident_executor_is_bit_identical_to_the_graph(cg, case):
+    """vm_kernel.cu: one resident CTA walking the whole tape (iteration loop inside the kernel) must give the same bits
+    as the per-step kernels replayed as a CUDA graph — root value of every iteration and every leaf."""
+    res = []
+    for dim in (0, 48):
+        cg.set_vm_max_dim(dim)
+        args = {}
+        if case.startswith("c3"):
+            _, mode, d = case.split("_")
+            cg.set_mode(mode)
+            f = readme_lstm(cg, int(d[1:]))
+            lr, iters = 0.01, 12
+        elif case == "broadcast_avg":
+            # scalar <- matrix gradients (mean, Q5) and scalar-matrix broadcasts: main.rs:133-154
+            F = cg.Function
+            x = F.scalar_param("x", 0.5)
+            m = F.param("m", cg.Constant(np.arange(12, dtype=np.float32).reshape(3, 4) / 7 - 0.6))
+            b = F.matrix(3, 4, list(np.linspace(-1, 1.5, 12)))
+            f = (((x - F.scalar(2.)) * (m + b) - F.scalar(10.)).sq() + (x * m).tanh()).abs()
+            lr, iters = 0.004, 15
+        else:
+            F = cg.Function
+            w = F.param("w", cg.Constant(np.linspace(-1, 1, 30, dtype=np.float32).reshape(6, 5)))
+            f = ((cg.dot(F.input("x", [8, 6]), w)).sigmoid() * F.input("s", []) - F.input("t", [8, 5])).sq()
+            rng = np.random.default_rng(3)
+            args = {"x": cg.Constant(rng.uniform(-1, 1, (8, 6)).astype(np.float32)), "s": cg.Constant.Scalar(1.5),
+                    "t": cg.Constant(rng.uniform(-1, 1, (8, 5)).astype(np.float32))}
+            lr, iters = 0.05, 9
+        st = cg.plan_stats(f, lr)
+        assert st["vm_resident"] == (1 if dim else 0)
+        l0 = cg.launch_count()
+        tr = np.array(f.minimize(args, lr, iters, trace=True))
+        launched = cg.launch_count() - l0
+        tr2 = np.array(f.minimize(args, lr, 3, 2, trace=True))  # print_freq = 2: the loop is cut at every print
+        res.append((tr, tr2, leaves_dict(f), np.asarray(f.value())))
+        if dim:
+            assert launched <= 1 + len(args)  # ONE kernel for all iterations (+ the layout kernel of a matrix input)
+    cg.set_mode("exact")
+    a, b = res
+    assert a[0].shape == b[0].shape and np.array_equal(a[0].view(np.int32), b[0].view(np.int32))
+    assert np.array_equal(a[1].view(np.int32), b[1].view(np.int32))
+    assert np.array_equal(a[3].view(np.int32), b[3].view(np.int32))
+    for k in a[2]:
+        assert np.array_equal(np.asarray(a[2][k]).view(np.int32), np.asarray(b[2][k]).view(np.int32)), k
+
+
 def test_medium_lstm_tiled_gemm(cg, oracle):
     """Products above the strict-kernel limit take the tiled FP32 SIMT kernel (FMA accumulation): 1e-5."""
     cg.set_mode("dag")
@@ -267,6 +314,7 @@ def test_host_transfers_inside_the_iteration_graph(cg, oracle):
         return traces, more, leaves_dict(f)
 
     keep = []
+    cg.set_vm_max_dim(0)  # these shapes would otherwise run on the resident executor, which has no transfer graph
     launches0 = cg.launch_count()
     try:
         got = run(cg, True, True)

@@ -41,6 +41,9 @@ def test_c3_kernel_counts(plans):
     assert (ex["gemms"], ex["gemms_fused_sgd"], ex["kernels_per_iter"]) == (72, 39, 103)
     assert (dag["gemms"], dag["gemms_fused_sgd"], dag["kernels_per_iter"]) == (35, 15, 52)
     assert dag["gemm_flop_per_iter"] == 35 * 2 * 30 ** 3
+    # latency-bound plans go to the resident tape executor (one CTA, one launch for all iterations); C4 never does
+    assert ex["vm_resident"] == 1 and dag["vm_resident"] == 1 and plans["c1"]["vm_resident"] == 1
+    assert plans["c4_hoist1"]["vm_resident"] == 0
 
 
 def test_c4_plan(plans):

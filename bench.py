@@ -342,8 +342,12 @@ def main():
                      "kernel": f"largest product, {gcnt.value} launches/iter, {gflop.value / 1e9:.1f} GFLOP each, "
                                f"{gms.value * 1e3:.1f} us avg (CUDA events around each launch, eager pass)",
                      "peak_source": peak_note,
-                     "whole_step": {"tflops": FLOP_PER_ITER_PER_GPU / (ms * 1e-3) / 1e12,
-                                    "frac": FLOP_PER_ITER_PER_GPU / (ms * 1e-3) / 1e12 / peak}},
+                     # every product the plan actually launches (dead products of the last step's output gate are
+                     # eliminated: 5.12 TFLOP) over the whole step; `survey_model` is SURVEY §8d's closed form
+                     "whole_step": {"tflops": stats["gemm_flop_per_iter"] / (ms * 1e-3) / 1e12,
+                                    "frac": stats["gemm_flop_per_iter"] / (ms * 1e-3) / 1e12 / peak,
+                                    "flop_per_iter": stats["gemm_flop_per_iter"],
+                                    "survey_model_flop_per_iter": FLOP_PER_ITER_PER_GPU}},
         "kernel_share": {"elementwise_ms": kind_ms[0], "reduce_ms": kind_ms[1], "product_ms": kind_ms[2],
                          "allreduce_ms": kind_ms[3], "instrumented_total_ms": total_ms,
                          "kernels": {"elementwise": int(kind_cnt[0]), "reduce": int(kind_cnt[1]),

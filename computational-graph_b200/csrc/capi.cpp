@@ -212,6 +212,13 @@ void cg_set_vm_max_dim(int v) {
     rt.vm_max_dim = v;
   });
 }
+void cg_set_tape_jit(int v) {
+  guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    if (rt.tape_jit != v) rt.dp_epoch++;  // the executor choice is part of a compiled plan
+    rt.tape_jit = v;
+  });
+}
 void cg_set_hoist(int v) {
   guard_rc([&] {
     Runtime& rt = Runtime::get();
@@ -252,6 +259,7 @@ int cg_plan_stats_get(cg_function* f, float lr, cg_plan_stats* out) {
     out->allreduces = s.allreduces;
     out->dp_fused_updates = s.dp_fused_updates;
     out->vm_resident = s.vm_resident;
+    out->tape_smem_bytes = s.tape_smem_bytes;
   });
 }
 long long cg_plan_describe(cg_function* f, float lr, char* buf, unsigned long long cap) {

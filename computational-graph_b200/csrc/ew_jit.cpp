@@ -12,12 +12,16 @@
 #include <cuda.h>
 #include <dlfcn.h>
 
+#include <algorithm>
+#include <cstring>
+#include <functional>
 #include <mutex>
+#include <set>
 #include <sstream>
 #include <unordered_map>
 #include <vector>
 
-#include "cg_common.h"
+#include "tape.h"
 
 namespace cg {
 
@@ -102,6 +106,63 @@ __device__ __forceinline__ float ew_sgn_scalar(float x) {
 }
 )SRC";
 
+// Operand spelling of one program: where input k / output k live and how immediate k is written. The per-kernel
+// specialiser reads them from the EwProgram kernel parameter; the tape specialiser bakes shared-memory offsets and
+// literal constants in.
+struct EwOperands {
+  std::function<std::string(uint32_t)> in, out, imm;
+};
+
+// Emits, at the current position of `s`, the straight-line code of program `p` for the float4 at element offset `b`
+// of a domain of `n` elements (both are names in scope). Scalar operands are expected in `s<k>`.
+void emit_ew_body(std::ostringstream& s, const EwProgram& p, const EwOperands& o, const char* ind, int vec = 4) {
+  // vec = 4: one float4 per thread (FOR4 / ld4 / st4); vec = 1: one element per thread (FOR1 / ld1 / st1), for
+  // domains so small that spreading them over more threads beats instruction-level parallelism
+  const std::string V = std::to_string(vec), FOR = "FOR" + V + " ", LD = "ld" + V + "(", ST = "st" + V + "(";
+  bool declared[EW_REGS] = {};
+  // inputs first: every load is issued before the first dependent instruction
+  for (uint32_t k = 0; k < p.n_in; k++) {
+    s << ind << "float r" << k << "[" << V << "];\n";
+    declared[k] = true;
+    if ((p.in_scalar_mask >> k) & 1u) s << ind << FOR << "r" << k << "[j] = s" << k << ";\n";
+    else s << ind << LD << o.in(k) << ", b, n, r" << k << ");\n";
+  }
+  s << ind << "float a[" << V << "] = {};\n";
+  for (uint32_t pc = 0; pc < p.n_ins; pc++) {
+    const unsigned ins = p.code[pc], op = ins >> 4, k = ins & 15u;
+    auto reg = [&](bool write) {
+      if (k >= (unsigned)EW_REGS) throw Error("internal: elementwise register out of range");
+      if (!declared[k]) {
+        if (!write) throw Error("internal: elementwise register read before write");
+        s << ind << "float r" << k << "[" << V << "];\n";
+        declared[k] = true;
+      }
+    };
+    s << ind;
+    switch (op) {
+      case OP_LDR: reg(false); s << FOR << "a[j] = r" << k << "[j];\n"; break;
+      case OP_STR: reg(true); s << FOR << "r" << k << "[j] = a[j];\n"; break;
+      case OP_LDI: s << FOR << "a[j] = " << o.imm(k) << ";\n"; break;
+      case OP_ADD: reg(false); s << FOR << "a[j] = __fadd_rn(a[j], r" << k << "[j]);\n"; break;
+      case OP_SUB: reg(false); s << FOR << "a[j] = __fsub_rn(a[j], r" << k << "[j]);\n"; break;
+      case OP_RSUB: reg(false); s << FOR << "a[j] = __fsub_rn(r" << k << "[j], a[j]);\n"; break;
+      case OP_MUL: reg(false); s << FOR << "a[j] = __fmul_rn(a[j], r" << k << "[j]);\n"; break;
+      case OP_MULI: s << FOR << "a[j] = __fmul_rn(a[j], " << o.imm(k) << ");\n"; break;
+      case OP_NEG: s << FOR << "a[j] = -a[j];\n"; break;
+      case OP_SQ: s << FOR << "a[j] = __fmul_rn(a[j], a[j]);\n"; break;
+      case OP_ABS_M: s << FOR << "a[j] = a[j] < 0.0f ? -a[j] : a[j];\n"; break;
+      case OP_SGN_M: s << FOR << "a[j] = a[j] < 0.0f ? -1.0f : 1.0f;\n"; break;
+      case OP_ABS_S: s << FOR << "a[j] = fabsf(a[j]);\n"; break;
+      case OP_SGN_S: s << FOR << "a[j] = ew_sgn_scalar(a[j]);\n"; break;
+      case OP_SIGMOID: s << FOR << "a[j] = ew_sigmoid(a[j]);\n"; break;
+      case OP_TANH: s << FOR << "a[j] = tanhf(a[j]);\n"; break;
+      case OP_ONE_MINUS: s << FOR << "a[j] = __fsub_rn(1.0f, a[j]);\n"; break;
+      case OP_STG: s << ST << o.out(k) << ", b, n, a);\n"; break;
+      default: throw Error("internal: unknown elementwise opcode");
+    }
+  }
+}
+
 std::string generate_source(const EwProgram& p) {
   std::ostringstream s;
   s << kPreamble;
@@ -112,47 +173,11 @@ std::string generate_source(const EwProgram& p) {
   for (uint32_t k = 0; k < p.n_in; k++)
     if ((p.in_scalar_mask >> k) & 1u) s << "  const float s" << k << " = *p.in[" << k << "];\n";
   s << "  for (u64 b = ((u64)blockIdx.x * 256 + threadIdx.x) * 4; b < n; b += step) {\n";
-  bool declared[EW_REGS] = {};
-  // inputs first: every load is issued before the first dependent instruction
-  for (uint32_t k = 0; k < p.n_in; k++) {
-    s << "    float r" << k << "[4];\n";
-    declared[k] = true;
-    if ((p.in_scalar_mask >> k) & 1u) s << "    FOR4 r" << k << "[j] = s" << k << ";\n";
-    else s << "    ld4(p.in[" << k << "], b, n, r" << k << ");\n";
-  }
-  s << "    float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};\n";
-  for (uint32_t pc = 0; pc < p.n_ins; pc++) {
-    const unsigned ins = p.code[pc], op = ins >> 4, k = ins & 15u;
-    auto reg = [&](bool write) {
-      if (k >= (unsigned)EW_REGS) throw Error("internal: elementwise register out of range");
-      if (!declared[k]) {
-        if (!write) throw Error("internal: elementwise register read before write");
-        s << "    float r" << k << "[4];\n";
-        declared[k] = true;
-      }
-    };
-    switch (op) {
-      case OP_LDR: reg(false); s << "    FOR4 a[j] = r" << k << "[j];\n"; break;
-      case OP_STR: reg(true); s << "    FOR4 r" << k << "[j] = a[j];\n"; break;
-      case OP_LDI: s << "    FOR4 a[j] = p.imm[" << k << "];\n"; break;
-      case OP_ADD: reg(false); s << "    FOR4 a[j] = __fadd_rn(a[j], r" << k << "[j]);\n"; break;
-      case OP_SUB: reg(false); s << "    FOR4 a[j] = __fsub_rn(a[j], r" << k << "[j]);\n"; break;
-      case OP_RSUB: reg(false); s << "    FOR4 a[j] = __fsub_rn(r" << k << "[j], a[j]);\n"; break;
-      case OP_MUL: reg(false); s << "    FOR4 a[j] = __fmul_rn(a[j], r" << k << "[j]);\n"; break;
-      case OP_MULI: s << "    FOR4 a[j] = __fmul_rn(a[j], p.imm[" << k << "]);\n"; break;
-      case OP_NEG: s << "    FOR4 a[j] = -a[j];\n"; break;
-      case OP_SQ: s << "    FOR4 a[j] = __fmul_rn(a[j], a[j]);\n"; break;
-      case OP_ABS_M: s << "    FOR4 a[j] = a[j] < 0.0f ? -a[j] : a[j];\n"; break;
-      case OP_SGN_M: s << "    FOR4 a[j] = a[j] < 0.0f ? -1.0f : 1.0f;\n"; break;
-      case OP_ABS_S: s << "    FOR4 a[j] = fabsf(a[j]);\n"; break;
-      case OP_SGN_S: s << "    FOR4 a[j] = ew_sgn_scalar(a[j]);\n"; break;
-      case OP_SIGMOID: s << "    FOR4 a[j] = ew_sigmoid(a[j]);\n"; break;
-      case OP_TANH: s << "    FOR4 a[j] = tanhf(a[j]);\n"; break;
-      case OP_ONE_MINUS: s << "    FOR4 a[j] = __fsub_rn(1.0f, a[j]);\n"; break;
-      case OP_STG: s << "    st4(p.out[" << k << "], b, n, a);\n"; break;
-      default: throw Error("internal: unknown elementwise opcode");
-    }
-  }
+  EwOperands o;
+  o.in = [](uint32_t k) { return "p.in[" + std::to_string(k) + "]"; };
+  o.out = [](uint32_t k) { return "p.out[" + std::to_string(k) + "]"; };
+  o.imm = [](uint32_t k) { return "p.imm[" + std::to_string(k) + "]"; };
+  emit_ew_body(s, p, o, "    ");
   s << "  }\n}\n";
   return s.str();
 }
@@ -178,6 +203,8 @@ struct Driver {
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
                            void**, void**) = nullptr;
   CUresult (*Occupancy)(int*, CUfunction, int, size_t) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
 };
 
 Driver& driver() {
@@ -194,6 +221,8 @@ Driver& driver() {
     r.ModuleGetFunction = reinterpret_cast<decltype(r.ModuleGetFunction)>(get("cuModuleGetFunction"));
     r.LaunchKernel = reinterpret_cast<decltype(r.LaunchKernel)>(get("cuLaunchKernel"));
     r.Occupancy = reinterpret_cast<decltype(r.Occupancy)>(get("cuOccupancyMaxActiveBlocksPerMultiprocessor"));
+    r.FuncSetAttribute = reinterpret_cast<decltype(r.FuncSetAttribute)>(get("cuFuncSetAttribute"));
+    r.ModuleUnload = reinterpret_cast<decltype(r.ModuleUnload)>(get("cuModuleUnload"));
     return r;
   }();
   return d;
@@ -203,10 +232,10 @@ void drv_check(CUresult r, const char* what) {
   if (r != CUDA_SUCCESS) throw Error(std::string("CUDA driver error ") + std::to_string((int)r) + " in " + what);
 }
 
-std::vector<char> compile_cubin(const std::string& src) {
+std::vector<char> compile_cubin(const std::string& src, const char* name = "ew_jit.cu") {
   Nvrtc& n = nvrtc();
   nvrtcProgram prog = nullptr;
-  if (n.CreateProgram(&prog, src.c_str(), "ew_jit.cu", 0, nullptr, nullptr) != 0) throw Error("nvrtcCreateProgram failed");
+  if (n.CreateProgram(&prog, src.c_str(), name, 0, nullptr, nullptr) != 0) throw Error("nvrtcCreateProgram failed");
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
   const int rc = n.CompileProgram(prog, 3, opts);
   if (rc != 0) {
@@ -215,7 +244,7 @@ std::vector<char> compile_cubin(const std::string& src) {
     std::string log(ls, '\0');
     if (ls) n.GetProgramLog(prog, log.data());
     n.DestroyProgram(&prog);
-    throw Error("NVRTC failed to compile a fused elementwise program:\n" + log);
+    throw Error(std::string("NVRTC failed to compile ") + name + ":\n" + log);
   }
   size_t sz = 0;
   n.GetCUBINSize(prog, &sz);
@@ -273,6 +302,344 @@ void launch_ew_jit(const EwKernel* k, const EwProgram& p, cudaStream_t stream) {
   const size_t grid = tiles < wave ? tiles : wave;
   void* params[] = {const_cast<EwProgram*>(&p)};
   drv_check(driver().LaunchKernel(k->fn, (unsigned)grid, 1, 1, 256, 1, 1, 0, (CUstream)stream, params, nullptr), "cuLaunchKernel");
+}
+
+// =====================================================================================================================
+// Whole-tape specialisation: the resident executor of vm_kernel.cu, compiled.
+//
+// For a latency-bound plan (BASELINE config 3: the README LSTM, every matrix <= 30 x 30) the interpreter VM still
+// pays a dependent chain of global loads per step — step record, program, bytecode, operands out of L2 — about 1 us a
+// step. Here the plan is unrolled at plan time into ONE straight-line kernel: every step is inline code with its
+// shapes as compile-time constants, and EVERY VALUE OF THE PLAN — leaves, arena temporaries, the root — lives in the
+// CTA's shared memory for the whole `minimize` call (the README LSTM at d = 30 needs ~180 KB of the SM's 227 KB).
+// Leaves are loaded once when the kernel starts and written back once when it ends; in between an iteration touches
+// neither L2 nor HBM. Products are 2 x 2 register-blocked over shared-memory operands, every output still accumulated
+// k-ascending with separate multiply / add roundings (cpu/ops.cpp:103-114), so the bits are the per-step kernels'.
+// =====================================================================================================================
+struct TapeKernel {
+  CUmodule module = nullptr;
+  CUfunction fn = nullptr;
+  size_t smem_bytes = 0, cubin_bytes = 0;
+};
+
+namespace {
+
+constexpr int TAPE_THREADS = 512;
+constexpr size_t TAPE_SMEM_BUDGET = 224 * 1024;  // of the 227 KB a CTA may own on sm_100a
+
+const char* kTapePreamble = R"SRC(
+typedef unsigned long long u64;
+#define FOR4 _Pragma("unroll") for (int j = 0; j < 4; j++)
+#define T 512
+extern __shared__ __align__(16) float S[];
+__device__ __forceinline__ void ld4(const float* p, u64 b, u64 n, float (&d)[4]) {
+  if (b + 4 <= n) {
+    const float4 x = *reinterpret_cast<const float4*>(p + b);
+    d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+  } else {
+    FOR4 d[j] = (b + j < n) ? p[b + j] : 0.0f;
+  }
+}
+__device__ __forceinline__ void st4(float* p, u64 b, u64 n, const float (&s)[4]) {
+  if (b + 4 <= n) {
+    *reinterpret_cast<float4*>(p + b) = make_float4(s[0], s[1], s[2], s[3]);
+  } else {
+    FOR4 if (b + j < n) p[b + j] = s[j];
+  }
+}
+#define FOR1 for (int j = 0; j < 1; j++)
+__device__ __forceinline__ void ld1(const float* p, u64 b, u64, float (&d)[1]) { d[0] = p[b]; }
+__device__ __forceinline__ void st1(float* p, u64 b, u64, const float (&s)[1]) { p[b] = s[0]; }
+__device__ __forceinline__ float ew_sigmoid(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+__device__ __forceinline__ float ew_sgn_scalar(float x) {
+  if (x != x) return x;
+  return (__float_as_uint(x) >> 31) ? -1.0f : 1.0f;
+}
+__device__ __forceinline__ void cp_in(int off, const float* g, int n) {
+  for (int i = threadIdx.x; i < n; i += T) S[off + i] = g[i];
+}
+__device__ __forceinline__ void cp_out(float* g, int off, int n) {
+  for (int i = threadIdx.x; i < n; i += T) g[i] = S[off + i];
+}
+template <int EPI>
+__device__ __forceinline__ void put(int co, int ldc, int i, int j, float acc, float lr) {
+  float* c = S + co + j * ldc + i;
+  if (EPI == 1) *c = __fsub_rn(*c, __fmul_rn(acc, lr));  // optimize.rs:149-152: two roundings
+  else if (EPI == 2) *c = __fadd_rn(*c, acc);
+  else *c = acc;
+}
+// C(M x N) = op(A) . op(B) over shared memory, column-major, 2 x 2 outputs per thread; each output is the k-ascending
+// separate-rounding sum of the reference (cpu/ops.cpp:103-114). One instantiation per distinct product shape.
+template <bool TA, bool TB, int EPI, int M, int N, int K, int LDA, int LDB, int LDC>
+__device__ __noinline__ void gemm(int ao, int bo, int co, float lr, int shift) {
+  constexpr int MB = (M + 1) / 2, NB = (N + 1) / 2;
+  for (int o = (threadIdx.x + T - shift) & (T - 1); o < MB * NB; o += T) {
+    const int i0 = (o % MB) * 2, j0 = (o / MB) * 2;
+    const bool i1 = i0 + 1 < M, j1 = j0 + 1 < N;
+    const int ia = i1 ? i0 + 1 : i0, jb = j1 ? j0 + 1 : j0;  // clamped: the duplicate lane is computed, never stored
+    float c00 = 0.0f, c01 = 0.0f, c10 = 0.0f, c11 = 0.0f;
+#pragma unroll 5
+    for (int kk = 0; kk < K; kk++) {
+      const float a0 = S[ao + (TA ? i0 * LDA + kk : kk * LDA + i0)];
+      const float a1 = S[ao + (TA ? ia * LDA + kk : kk * LDA + ia)];
+      const float b0 = S[bo + (TB ? kk * LDB + j0 : j0 * LDB + kk)];
+      const float b1 = S[bo + (TB ? kk * LDB + jb : jb * LDB + kk)];
+      c00 = __fadd_rn(c00, __fmul_rn(a0, b0));
+      c01 = __fadd_rn(c01, __fmul_rn(a0, b1));
+      c10 = __fadd_rn(c10, __fmul_rn(a1, b0));
+      c11 = __fadd_rn(c11, __fmul_rn(a1, b1));
+    }
+    put<EPI>(co, LDC, i0, j0, c00, lr);
+    if (j1) put<EPI>(co, LDC, i0, j0 + 1, c01, lr);
+    if (i1) put<EPI>(co, LDC, i0 + 1, j0, c10, lr);
+    if (i1 && j1) put<EPI>(co, LDC, i0 + 1, j0 + 1, c11, lr);
+  }
+}
+// The same product with one output per thread: for shapes with M * N <= 512 every output gets its own thread and
+// the per-thread instruction count — what bounds a one-warp step — is a quarter of the blocked version's.
+template <bool TA, bool TB, int EPI, int M, int N, int K, int LDA, int LDB, int LDC>
+__device__ __noinline__ void gemm1(int ao, int bo, int co, float lr, int shift) {
+  for (int o = (threadIdx.x + T - shift) & (T - 1); o < M * N; o += T) {
+    const int i = o % M, j = o / M;
+    float acc = 0.0f;
+#pragma unroll 6
+    for (int kk = 0; kk < K; kk++)
+      acc = __fadd_rn(acc, __fmul_rn(S[ao + (TA ? i * LDA + kk : kk * LDA + i)], S[bo + (TB ? kk * LDB + j : j * LDB + kk)]));
+    put<EPI>(co, LDC, i, j, acc, lr);
+  }
+}
+)SRC";
+
+struct TapeBuf {
+  const float* ptr;
+  size_t n, off;
+  bool persistent, written;
+};
+
+std::string f32_literal(float v) {
+  uint32_t bits;
+  memcpy(&bits, &v, sizeof bits);
+  char buf[48];
+  snprintf(buf, sizeof buf, "__int_as_float(0x%08x)", bits);
+  return buf;
+}
+
+std::string ptr_literal(const void* p) {
+  char buf[48];
+  snprintf(buf, sizeof buf, "((float*)0x%llxULL)", (unsigned long long)(uintptr_t)p);
+  return buf;
+}
+
+// Lays every buffer the plan touches out in shared memory; false when the plan does not fit (or buffers overlap
+// in a way one flat layout cannot express).
+bool tape_layout(const Plan& p, std::vector<TapeBuf>& bufs, size_t& total_floats) {
+  std::unordered_map<const float*, size_t> index;
+  auto touch = [&](const float* ptr, size_t n, bool write) {
+    auto it = index.find(ptr);
+    if (it == index.end()) {
+      index[ptr] = bufs.size();
+      bufs.push_back(TapeBuf{ptr, n, 0, false, write});
+    } else {
+      TapeBuf& b = bufs[it->second];
+      b.n = std::max(b.n, n);
+      b.written |= write;
+    }
+  };
+  for (const Step& s : p.steps) {
+    if (s.kind == Step::EW) {
+      for (uint32_t k = 0; k < s.prog.n_in; k++) touch(s.prog.in[k], ((s.prog.in_scalar_mask >> k) & 1u) ? 1 : s.prog.n, false);
+      for (uint32_t k = 0; k < s.prog.n_out; k++) touch(s.prog.out[k], s.prog.n, true);
+    } else if (s.kind == Step::AVG) {
+      touch(p.vals[s.ins.a].ptr, p.vals[s.ins.a].sh.n(), false);
+      touch(p.vals[s.ins.dst].ptr, 1, true);
+    } else if (s.kind == Step::GEMM) {
+      touch(p.vals[s.ins.a].ptr, p.vals[s.ins.a].sh.n(), false);
+      touch(p.vals[s.ins.b].ptr, p.vals[s.ins.b].sh.n(), false);
+      touch(p.vals[s.ins.dst].ptr, p.vals[s.ins.dst].sh.n(), true);
+    } else {
+      return false;
+    }
+  }
+  touch(p.root_ptr, p.root_n, false);
+  // no partial overlaps (arena slots are recycled whole, leaves are separate allocations)
+  std::vector<const TapeBuf*> sorted;
+  for (const TapeBuf& b : bufs) sorted.push_back(&b);
+  std::sort(sorted.begin(), sorted.end(), [](const TapeBuf* a, const TapeBuf* b) { return a->ptr < b->ptr; });
+  for (size_t i = 0; i + 1 < sorted.size(); i++)
+    if (sorted[i]->ptr + sorted[i]->n > sorted[i + 1]->ptr) return false;
+  const float* alo = p.arena ? p.arena->ptr : nullptr;
+  const float* ahi = p.arena ? p.arena->ptr + p.arena->n : nullptr;
+  total_floats = 0;
+  for (TapeBuf& b : bufs) {
+    b.persistent = !(alo && b.ptr >= alo && b.ptr < ahi);
+    b.off = total_floats;
+    total_floats += (b.n + 3) / 4 * 4;
+  }
+  return total_floats * sizeof(float) <= TAPE_SMEM_BUDGET;
+}
+
+std::string tape_source(const Plan& p, const std::vector<TapeBuf>& bufs) {
+  std::unordered_map<const float*, const TapeBuf*> at;
+  for (const TapeBuf& b : bufs) at[b.ptr] = &b;
+  auto off = [&](const float* ptr) { return std::to_string(at.at(ptr)->off); };
+  std::ostringstream s;
+  s << kTapePreamble;
+  s << "extern \"C\" __global__ void __launch_bounds__(512, 1) tape_jit(int iters, float* trace) {\n"
+       "  const unsigned t = threadIdx.x;\n";
+  for (const TapeBuf& b : bufs)
+    if (b.persistent) s << "  cp_in(" << b.off << ", " << ptr_literal(b.ptr) << ", " << b.n << ");\n";
+  s << "  __syncthreads();\n"
+       "  for (int it = 0; it < iters; it++) {\n";
+  const std::string trace_copy = "    if (trace) {\n      cp_out(trace + (u64)it * " + std::to_string(p.root_n) + ", " + off(p.root_ptr) + ", " +
+                                 std::to_string(p.root_n) + ");\n      __syncthreads();\n    }\n";
+  // the traced value of an iteration is its forward value, before the update (Q12): a leaf root is read first
+  if (p.root_is_leaf) s << trace_copy;
+  // Steps are scheduled by dependency LEVEL (RAW / WAR / WAW on the buffers they touch, in tape order): a level is one
+  // phase between two __syncthreads(), so the barrier count is the critical path of the iteration, not its step count.
+  // Independent steps of one phase start at different threads (`shift`), so e.g. the gate products of an LSTM step run
+  // side by side instead of one after the other.
+  struct Access {
+    std::vector<const float*> rd, wr;
+    size_t items = 1;
+  };
+  const size_t nsteps = p.steps.size();
+  std::vector<Access> acc(nsteps);
+  for (size_t i = 0; i < nsteps; i++) {
+    const Step& st = p.steps[i];
+    Access& a = acc[i];
+    if (st.kind == Step::EW) {
+      for (uint32_t k = 0; k < st.prog.n_in; k++) a.rd.push_back(st.prog.in[k]);
+      for (uint32_t k = 0; k < st.prog.n_out; k++) a.wr.push_back(st.prog.out[k]);
+      a.items = st.prog.n <= (size_t)TAPE_THREADS ? st.prog.n : (st.prog.n + 3) / 4;
+    } else if (st.kind == Step::AVG) {
+      a.rd.push_back(p.vals[st.ins.a].ptr);
+      a.wr.push_back(p.vals[st.ins.dst].ptr);
+    } else {
+      a.rd.push_back(p.vals[st.ins.a].ptr);
+      a.rd.push_back(p.vals[st.ins.b].ptr);
+      if (st.ins.epi) a.rd.push_back(p.vals[st.ins.dst].ptr);
+      a.wr.push_back(p.vals[st.ins.dst].ptr);
+      const Shape& cs = p.vals[st.ins.dst].sh;
+      a.items = cs.n() <= (size_t)TAPE_THREADS ? cs.n() : (size_t)((cs.h + 1) / 2) * ((cs.w + 1) / 2);
+    }
+  }
+  std::vector<int> level(nsteps, 0);
+  {
+    struct Loc {
+      int last_writer = -1;
+      std::vector<int> readers;
+    };
+    std::unordered_map<const float*, Loc> loc;
+    for (size_t i = 0; i < nsteps; i++) {
+      int lv = 0;
+      auto dep = [&](int d) {
+        if (d >= 0) lv = std::max(lv, level[d] + 1);
+      };
+      for (const float* r : acc[i].rd) dep(loc[r].last_writer);
+      for (const float* w : acc[i].wr) {
+        Loc& l = loc[w];
+        dep(l.last_writer);
+        for (int rd : l.readers) dep(rd);
+      }
+      level[i] = lv;
+      for (const float* r : acc[i].rd) loc[r].readers.push_back((int)i);
+      for (const float* w : acc[i].wr) {
+        Loc& l = loc[w];
+        l.last_writer = (int)i;
+        l.readers.clear();
+      }
+    }
+  }
+  std::vector<size_t> order(nsteps);
+  for (size_t i = 0; i < nsteps; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return level[x] < level[y]; });
+  unsigned shift = 0;
+  int cur_level = 0;
+  for (size_t oi = 0; oi < nsteps; oi++) {
+    const size_t i = order[oi];
+    const Step& st = p.steps[i];
+    const size_t items = acc[i].items;
+    if (level[i] != cur_level) {
+      s << "    __syncthreads();\n";
+      cur_level = level[i];
+      shift = 0;
+    }
+    if (st.kind == Step::EW) {
+      const EwProgram& pr = st.prog;
+      s << "    {  // step " << i << ": elementwise, n = " << pr.n << "\n      const u64 n = " << pr.n << ";\n";
+      for (uint32_t k = 0; k < pr.n_in; k++)
+        if ((pr.in_scalar_mask >> k) & 1u) s << "      const float s" << k << " = S[" << off(pr.in[k]) << "];\n";
+      const int vec = pr.n <= (uint64_t)TAPE_THREADS ? 1 : 4;
+      s << "      for (u64 b = (u64)((t + T - " << shift << ") & (T - 1)) * " << vec << "; b < n; b += T * " << vec << ") {\n";
+      EwOperands o;
+      o.in = [&](uint32_t k) { return "S + " + off(pr.in[k]); };
+      o.out = [&](uint32_t k) { return "S + " + off(pr.out[k]); };
+      o.imm = [&](uint32_t k) { return f32_literal(pr.imm[k]); };
+      emit_ew_body(s, pr, o, "        ", vec);
+      s << "      }\n    }\n";
+    } else if (st.kind == Step::AVG) {
+      const Val& a = p.vals[st.ins.a];
+      s << "    if (t == " << shift << ") {  // step " << i << ": scalar <- matrix mean, sequential sum (cpu/ops.cpp:138-145)\n"
+        << "      float sum = 0.0f;\n      for (int i = 0; i < " << a.sh.n() << "; i++) sum = __fadd_rn(sum, S[" << off(a.ptr) << " + i]);\n"
+        << "      S[" << off(p.vals[st.ins.dst].ptr) << "] = __fdiv_rn(sum, " << f32_literal((float)a.sh.n()) << ");\n    }\n";
+    } else {
+      const Val &a = p.vals[st.ins.a], &b = p.vals[st.ins.b], &c = p.vals[st.ins.dst];
+      const int m = (int)c.sh.h, n = (int)c.sh.w, k = (int)(st.ins.ta ? a.sh.h : a.sh.w);
+      if (st.ins.epi && p.vals[st.ins.c_in].ptr != c.ptr) throw Error("internal: gemm epilogue operand is not in place");
+      s << "    " << (c.sh.n() <= (size_t)TAPE_THREADS ? "gemm1<" : "gemm<") << (st.ins.ta ? "true" : "false") << ", " << (st.ins.tb ? "true" : "false") << ", " << st.ins.epi << ", " << m
+        << ", " << n << ", " << k << ", " << a.sh.h << ", " << b.sh.h << ", " << c.sh.h << ">(" << off(a.ptr) << ", " << off(b.ptr)
+        << ", " << off(c.ptr) << ", " << f32_literal(st.ins.imm) << ", " << shift << ");  // step " << i << "\n";
+    }
+    shift = (unsigned)(((shift + items + 31) / 32 * 32) % TAPE_THREADS);  // the next step of this phase starts on a fresh warp
+  }
+  s << "    __syncthreads();\n";
+  if (!p.root_is_leaf) s << trace_copy;
+  s << "  }\n";
+  for (const TapeBuf& b : bufs)
+    if (b.persistent && b.written) s << "  cp_out(" << ptr_literal(b.ptr) << ", " << b.off << ", " << b.n << ");\n";
+  s << "}\n";
+  return s.str();
+}
+
+}  // namespace
+
+const TapeKernel* tape_jit_build(const Plan& p, bool load) {
+  if (!nvrtc().ok || p.steps.empty()) return nullptr;
+  std::vector<TapeBuf> bufs;
+  size_t total = 0;
+  if (!tape_layout(p, bufs, total)) return nullptr;
+  const std::string src = tape_source(p, bufs);
+  if (const char* path = getenv("CG_TAPE_JIT_DUMP")) {
+    if (FILE* f = fopen(path, "w")) {
+      fputs(src.c_str(), f);
+      fclose(f);
+    }
+  }
+  const std::vector<char> cubin = compile_cubin(src, "tape_jit.cu");
+  auto* k = new TapeKernel();
+  k->smem_bytes = total * sizeof(float);
+  k->cubin_bytes = cubin.size();
+  if (!load) return k;
+  CG_CUDA(cudaFree(nullptr));  // make sure the primary context is current on this thread
+  drv_check(driver().ModuleLoadData(&k->module, cubin.data()), "cuModuleLoadData");
+  drv_check(driver().ModuleGetFunction(&k->fn, k->module, "tape_jit"), "cuModuleGetFunction");
+  drv_check(driver().FuncSetAttribute(k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)k->smem_bytes), "cuFuncSetAttribute");
+  return k;
+}
+
+void tape_jit_free(const TapeKernel* k) {
+  if (!k) return;
+  if (k->module) driver().ModuleUnload(k->module);
+  delete k;
+}
+
+size_t tape_jit_smem_bytes(const TapeKernel* k) { return k ? k->smem_bytes : 0; }
+
+void launch_tape_jit(const TapeKernel* k, int iters, float* trace, cudaStream_t stream) {
+  if (iters <= 0) return;
+  void* params[] = {&iters, &trace};
+  drv_check(driver().LaunchKernel(k->fn, 1, 1, 1, TAPE_THREADS, 1, 1, (unsigned)k->smem_bytes, (CUstream)stream, params, nullptr),
+            "cuLaunchKernel");
 }
 
 }  // namespace cg

@@ -315,7 +315,7 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
     cudaEventRecord(dbg_ev[0], rt.stream);
   }
   // One iteration whose host transfers ride inside the graph (pinned buffers only); otherwise: upload, then loop.
-  const bool vm = p.vm_steps != nullptr;
+  const bool vm = p.vm_steps != nullptr || p.tape_kernel != nullptr;
   const bool io = !vm && !reuse_inputs && iters >= 1 && (iters == 1 || !trace) && io_graph_eligible(p, rt, args, trace);
   if (!reuse_inputs && !io) upload_inputs(p, args);
   if (dbg) cudaEventRecord(dbg_ev[1], rt.stream);
@@ -332,8 +332,9 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
     while (done < iters) {
       int chunk = iters - done;
       if (print_freq > 0) chunk = std::min(chunk, print_freq - done % print_freq);
-      launch_tape_vm(p.vm_steps, p.vm_progs, p.vm_nsteps, chunk, p.root_ptr, p.root_n, p.root_is_leaf,
-                     trace_dev ? trace_dev + (size_t)done * p.root_n : nullptr, rt.stream);
+      float* tr = trace_dev ? trace_dev + (size_t)done * p.root_n : nullptr;
+      if (p.tape_kernel) launch_tape_jit(p.tape_kernel, chunk, tr, rt.stream);
+      else launch_tape_vm(p.vm_steps, p.vm_progs, p.vm_nsteps, chunk, p.root_ptr, p.root_n, p.root_is_leaf, tr, rt.stream);
       rt.launches++;
       done += chunk;
       if (print_freq > 0 && done % print_freq == 0) print_value(f.value);

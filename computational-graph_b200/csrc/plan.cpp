@@ -18,6 +18,7 @@
 namespace cg {
 
 Plan::~Plan() {
+  tape_jit_free(tape_kernel);
   if (vm_steps) cudaFree(vm_steps);
   if (vm_progs) cudaFree(vm_progs);
   release_graphs();
@@ -1002,17 +1003,21 @@ void build_vm(Plan& p) {
   const size_t max_elems = (size_t)rt.vm_max_dim * rt.vm_max_dim;
   std::vector<VmStep> steps;
   std::vector<EwProgram> progs;
+  int dim_seen = 0;
+  size_t elems_seen = 0;
   for (const Step& s : p.steps) {
     VmStep v;
     memset(&v, 0, sizeof v);
     if (s.kind == Step::EW) {
       if (s.prog.n > max_elems) return;
+      elems_seen = std::max<size_t>(elems_seen, s.prog.n);
       v.kind = VmStep::EW;
       v.prog = (int)progs.size();
       progs.push_back(s.prog);
     } else if (s.kind == Step::AVG) {
       const Val& a = p.vals[s.ins.a];
       if (a.sh.n() > kStrictReduceMax || a.sh.n() > max_elems) return;
+      elems_seen = std::max(elems_seen, a.sh.n());
       v.kind = VmStep::AVG;
       v.n = (int)a.sh.n();
       v.a = a.ptr;
@@ -1022,6 +1027,7 @@ void build_vm(Plan& p) {
       v.kind = VmStep::GEMM;
       v.m = (int)c.sh.h, v.n = (int)c.sh.w, v.k = (int)(s.ins.ta ? a.sh.h : a.sh.w);
       if (std::max(v.m, std::max(v.n, v.k)) > max_dim) return;
+      dim_seen = std::max(dim_seen, std::max(v.m, std::max(v.n, v.k)));
       if (s.ins.epi && p.vals[s.ins.c_in].ptr != c.ptr) throw Error("internal: gemm epilogue operand is not in place");
       v.lda = (int)a.sh.h, v.ldb = (int)b.sh.h, v.ldc = (int)c.sh.h;
       v.ta = s.ins.ta, v.tb = s.ins.tb, v.epi = s.ins.epi;
@@ -1032,6 +1038,18 @@ void build_vm(Plan& p) {
     }
     steps.push_back(v);
   }
+  // 1. compiled, shared-memory resident (ew_jit.cpp): whenever the plan's values fit in one SM's shared memory
+  if (rt.tape_jit) {
+    p.tape_kernel = tape_jit_build(p, !plan_only());
+    if (p.tape_kernel) {
+      p.stats.vm_resident = 2;
+      p.stats.tape_smem_bytes = tape_jit_smem_bytes(p.tape_kernel);
+      return;
+    }
+  }
+  // 2. interpreted, values in L1 / L2 (vm_kernel.cu): measured faster than the CUDA graph up to d = 20 on the README
+  //    LSTM (155 vs 203 us per iteration), slower from d = 25 on
+  if (dim_seen > 20 || elems_seen > 400) return;
   p.stats.vm_resident = 1;
   if (plan_only()) return;
   p.vm_nsteps = (int)steps.size();

@@ -88,9 +88,18 @@ struct VmStep {
 void launch_tape_vm(const VmStep* steps, const EwProgram* progs, int nsteps, int iters, const float* root, size_t root_n,
                     bool root_is_leaf, float* trace, cudaStream_t stream);
 
+// The whole plan compiled into one resident kernel with every value in shared memory (ew_jit.cpp, NVRTC); nullptr when
+// the plan does not fit in one SM's shared memory or libnvrtc is absent. load = false compiles without a device.
+struct TapeKernel;
+struct Plan;
+const TapeKernel* tape_jit_build(const Plan& p, bool load);
+void tape_jit_free(const TapeKernel* k);
+size_t tape_jit_smem_bytes(const TapeKernel* k);
+void launch_tape_jit(const TapeKernel* k, int iters, float* trace, cudaStream_t stream);
+
 struct PlanStats {
   size_t tape_instrs = 0, live_instrs = 0, ew_groups = 0, gemms = 0, gemms_fused_sgd = 0, reduces = 0;
-  size_t arena_bytes = 0, kernels_per_iter = 0, ew_specialised = 0, allreduces = 0, dp_fused_updates = 0, vm_resident = 0;
+  size_t arena_bytes = 0, kernels_per_iter = 0, ew_specialised = 0, allreduces = 0, dp_fused_updates = 0, vm_resident = 0, tape_smem_bytes = 0;
   double gemm_flop_per_iter = 0.0, ew_bytes_per_iter = 0.0;
 };
 
@@ -129,6 +138,7 @@ struct Plan {
   IoGraph io[2];                    // [0] without, [1] with the D2H read of the root value
   std::vector<BufRef> io_staging;   // row-major landing buffer per matrix input
   // resident tape executor (vm_kernel.cu): the steps and programs in device memory, when the plan is small enough
+  const TapeKernel* tape_kernel = nullptr;  // the compiled form (shared-memory resident), preferred when present
   VmStep* vm_steps = nullptr;
   EwProgram* vm_progs = nullptr;
   int vm_nsteps = 0;

@@ -104,6 +104,10 @@ void cg_set_hoist(int on);
  * limit) — are executed by ONE resident CTA that walks the whole tape, iteration loop included, instead of one CUDA-graph
  * node per step (vm_kernel.cu; same arithmetic, same bits). Default 48 (covers the README LSTM sweep, d <= 30); 0: never. */
 void cg_set_vm_max_dim(int dim);
+/* 1 (default): a resident plan whose values all fit in one SM's shared memory (<= 224 KB) is compiled at plan time
+ * (NVRTC) into ONE straight-line kernel — shapes as constants, every leaf and temporary in shared memory for the
+ * whole minimize call, leaves loaded once and written back once. 0: the interpreting executor / the CUDA graph. */
+void cg_set_tape_jit(int on);
 
 /* ---- introspection -------------------------------------------------------------------------------- */
 typedef struct {
@@ -113,7 +117,8 @@ typedef struct {
   unsigned long long ew_specialised; /* elementwise kernels compiled to straight-line code (cg_set_ew_jit_min) */
   unsigned long long allreduces;       /* data parallel: weight gradients summed with ncclAllReduce */
   unsigned long long dp_fused_updates; /* data parallel: all-reduce + SGD update as one peer-memory kernel */
-  unsigned long long vm_resident;      /* 1: the plan runs on the resident tape executor (cg_set_vm_max_dim) */
+  unsigned long long vm_resident;      /* resident executor: 0 none (CUDA graph), 1 interpreting (vm_kernel.cu), 2 compiled */
+  unsigned long long tape_smem_bytes;  /* compiled resident kernel: shared memory holding every value of the plan */
 } cg_plan_stats;
 int cg_plan_stats_get(cg_function *f, float learn_rate, cg_plan_stats *out); /* compiles the plan if needed */
 /* One text line per kernel of the compiled iteration, in launch order ("<i> GEMM m= n= k= ta= tb= epi=", "<i> EW n= in= out=

@@ -41,4 +41,5 @@ def cg():
     api.set_tf32_pair(False)
     api.set_hoist(True)
     api.set_vm_max_dim(48)
+    api.set_tape_jit(True)
     return api

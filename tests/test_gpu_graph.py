@@ -154,11 +154,15 @@ def test_hoisting_is_bit_identical(cg, tf32, shape):
 
 @pytest.mark.parametrize("case", ["c3_exact_d5", "c3_exact_d30", "c3_dag_d30", "broadcast_avg", "inputs"])
 def test_resident_executor_is_bit_identical_to_the_graph(cg, case):
-    """vm_kernel.cu: one resident CTA walking the whole tape (iteration loop inside the kernel) must give the same bits
-    as the per-step kernels replayed as a CUDA graph — root value of every iteration and every leaf."""
+    """The resident executors — one CTA running the whole tape with the iteration loop inside the kernel, either
+    interpreting it out of L1/L2 (vm_kernel.cu) or compiled with every value in shared memory (ew_jit.cpp tape_jit) —
+    must give the same bits as the per-step kernels replayed as a CUDA graph: root value of every iteration, every
+    leaf."""
     res = []
-    for dim in (0, 48):
+    for executor in ("graph", "interpreted", "compiled"):
+        dim = 0 if executor == "graph" else 48
         cg.set_vm_max_dim(dim)
+        cg.set_tape_jit(executor == "compiled")
         args = {}
         if case.startswith("c3"):
             _, mode, d = case.split("_")
@@ -182,21 +186,26 @@ def test_resident_executor_is_bit_identical_to_the_graph(cg, case):
                     "t": cg.Constant(rng.uniform(-1, 1, (8, 5)).astype(np.float32))}
             lr, iters = 0.05, 9
         st = cg.plan_stats(f, lr)
-        assert st["vm_resident"] == (1 if dim else 0)
+        small = case != "c3_exact_d30" and case != "c3_dag_d30"  # the interpreter only takes plans with d <= 20
+        want = {"graph": 0, "interpreted": 1 if small else 0, "compiled": 2}[executor]
+        assert st["vm_resident"] == want, st
+        assert (st["tape_smem_bytes"] > 0) == (executor == "compiled")
         l0 = cg.launch_count()
         tr = np.array(f.minimize(args, lr, iters, trace=True))
         launched = cg.launch_count() - l0
         tr2 = np.array(f.minimize(args, lr, 3, 2, trace=True))  # print_freq = 2: the loop is cut at every print
         res.append((tr, tr2, leaves_dict(f), np.asarray(f.value())))
-        if dim:
+        if want:
             assert launched <= 1 + len(args)  # ONE kernel for all iterations (+ the layout kernel of a matrix input)
     cg.set_mode("exact")
-    a, b = res
-    assert a[0].shape == b[0].shape and np.array_equal(a[0].view(np.int32), b[0].view(np.int32))
-    assert np.array_equal(a[1].view(np.int32), b[1].view(np.int32))
-    assert np.array_equal(a[3].view(np.int32), b[3].view(np.int32))
-    for k in a[2]:
-        assert np.array_equal(np.asarray(a[2][k]).view(np.int32), np.asarray(b[2][k]).view(np.int32)), k
+    cg.set_tape_jit(True)
+    a = res[0]
+    for b in res[1:]:
+        assert a[0].shape == b[0].shape and np.array_equal(a[0].view(np.int32), b[0].view(np.int32))
+        assert np.array_equal(a[1].view(np.int32), b[1].view(np.int32))
+        assert np.array_equal(a[3].view(np.int32), b[3].view(np.int32))
+        for k in a[2]:
+            assert np.array_equal(np.asarray(a[2][k]).view(np.int32), np.asarray(b[2][k]).view(np.int32)), k
 
 
 def test_medium_lstm_tiled_gemm(cg, oracle):

@@ -38,7 +38,8 @@ class PlanStats(C.Structure):
     _fields_ = [(n, C.c_ulonglong) for n in ("tape_instrs", "live_instrs", "kernels_per_iter", "ew_kernels", "gemms",
                                              "gemms_fused_sgd", "reduces", "arena_bytes")] + \
                [("gemm_flop_per_iter", C.c_double), ("ew_bytes_per_iter", C.c_double), ("ew_specialised", C.c_ulonglong),
-                ("allreduces", C.c_ulonglong), ("dp_fused_updates", C.c_ulonglong), ("vm_resident", C.c_ulonglong), ("tape_smem_bytes", C.c_ulonglong)]
+                ("allreduces", C.c_ulonglong), ("dp_fused_updates", C.c_ulonglong), ("vm_resident", C.c_ulonglong), ("tape_smem_bytes", C.c_ulonglong),
+                ("quiet_variant", C.c_ulonglong), ("quiet_ew_bytes_per_iter", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -50,7 +51,7 @@ class ProductApi(Api):
     def __init__(self, lib: C.CDLL):
         super().__init__(lib, "cg_")
         for name in ("set_tf32", "set_fix_act_grad", "set_fuse", "set_cuda_graph", "set_strict_gemm_max",
-                     "set_graph_streams", "set_io_graph", "set_tf32_pair", "set_hoist", "set_vm_max_dim", "set_tape_jit"):
+                     "set_graph_streams", "set_io_graph", "set_tf32_pair", "set_hoist", "set_vm_max_dim", "set_tape_jit", "set_elide_root"):
             fn = self._sym(name)
             fn.restype, fn.argtypes = None, [C.c_int]
         lib.cg_launch_count.restype = C.c_ulonglong
@@ -118,6 +119,7 @@ class ProductApi(Api):
     def set_hoist(self, on: bool): self.lib.cg_set_hoist(int(on))
     def set_vm_max_dim(self, dim: int): self.lib.cg_set_vm_max_dim(int(dim))
     def set_tape_jit(self, on: bool): self.lib.cg_set_tape_jit(int(on))
+    def set_elide_root(self, on: bool): self.lib.cg_set_elide_root(int(on))
     def set_device(self, dev: int): self._check(self.lib.cg_set_device(int(dev)))
     def launch_count(self) -> int: return int(self.lib.cg_launch_count())
     def synchronize(self): self._check(self.lib.cg_synchronize())

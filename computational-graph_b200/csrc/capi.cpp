@@ -212,6 +212,13 @@ void cg_set_vm_max_dim(int v) {
     rt.vm_max_dim = v;
   });
 }
+void cg_set_elide_root(int v) {
+  guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    if (rt.elide_root != v) rt.dp_epoch++;
+    rt.elide_root = v;
+  });
+}
 void cg_set_tape_jit(int v) {
   guard_rc([&] {
     Runtime& rt = Runtime::get();
@@ -260,6 +267,8 @@ int cg_plan_stats_get(cg_function* f, float lr, cg_plan_stats* out) {
     out->dp_fused_updates = s.dp_fused_updates;
     out->vm_resident = s.vm_resident;
     out->tape_smem_bytes = s.tape_smem_bytes;
+    out->quiet_variant = s.quiet_variant;
+    out->quiet_ew_bytes_per_iter = s.quiet_ew_bytes_per_iter;
   });
 }
 long long cg_plan_describe(cg_function* f, float lr, char* buf, unsigned long long cap) {

@@ -292,6 +292,26 @@ void launch_io_graph(Plan& p, Runtime& rt, const std::vector<Arg>& args, float* 
 
 }  // namespace
 
+// Captures the iteration of `p` as a CUDA graph (a DAG over side streams, or one linear stream) if it is not yet.
+static void ensure_graph(Plan& p, Runtime& rt) {
+  if (!rt.use_graph || p.graph_exec || p.steps.empty()) return;
+  if (rt.graph_streams > 0) {
+    capture_dag(p, rt);
+    return;
+  }
+  CG_CUDA(cudaStreamBeginCapture(rt.stream, cudaStreamCaptureModeThreadLocal));
+  try {
+    plan_launch_iteration(p, rt.stream);
+  } catch (...) {
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(rt.stream, &g);
+    if (g) cudaGraphDestroy(g);
+    throw;
+  }
+  CG_CUDA(cudaStreamEndCapture(rt.stream, &p.graph));
+  CG_CUDA(cudaGraphInstantiate(&p.graph_exec, p.graph, 0));
+}
+
 void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, int print_freq, float* trace,
               bool synchronize, bool reuse_inputs) {
   Runtime& rt = Runtime::get();
@@ -347,21 +367,8 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
     if (synchronize) CG_CUDA(cudaStreamSynchronize(rt.stream));
     return;
   }
-  if (rt.use_graph && !p.graph_exec && !p.steps.empty() && rt.graph_streams > 0) {
-    capture_dag(p, rt);
-  } else if (rt.use_graph && !p.graph_exec && !p.steps.empty()) {
-    CG_CUDA(cudaStreamBeginCapture(rt.stream, cudaStreamCaptureModeThreadLocal));
-    try {
-      plan_launch_iteration(p, rt.stream);
-    } catch (...) {
-      cudaGraph_t g = nullptr;
-      cudaStreamEndCapture(rt.stream, &g);
-      if (g) cudaGraphDestroy(g);
-      throw;
-    }
-    CG_CUDA(cudaStreamEndCapture(rt.stream, &p.graph));
-    CG_CUDA(cudaGraphInstantiate(&p.graph_exec, p.graph, 0));
-  }
+  ensure_graph(p, rt);
+  if (p.quiet) ensure_graph(*p.quiet, rt);
 
   float* trace_dev = nullptr;
   const bool direct_trace = trace && iters == 1;  // one iteration: read the root value straight back
@@ -378,9 +385,13 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
     if (trace_dev && p.root_is_leaf)
       CG_CUDA(cudaMemcpyAsync(trace_dev + (size_t)i * p.root_n, p.root_ptr, p.root_n * sizeof(float),
                               cudaMemcpyDeviceToDevice, rt.stream));
-    if (p.graph_exec) CG_CUDA(cudaGraphLaunch(p.graph_exec, rt.stream));
-    else plan_launch_iteration(p, rt.stream);
-    rt.launches += p.steps.size();
+    // Only the LAST iteration's root value is observable after the call (Q12) unless it is traced or printed: the
+    // others run the variant of the plan that does not materialise it (build_plan, `quiet`).
+    const bool observed = i == iters - 1 || trace_dev || (print_freq > 0 && (i + 1) % print_freq == 0);
+    Plan& q = (p.quiet && !observed) ? *p.quiet : p;
+    if (q.graph_exec) CG_CUDA(cudaGraphLaunch(q.graph_exec, rt.stream));
+    else plan_launch_iteration(q, rt.stream);
+    rt.launches += q.steps.size();
     if (trace_dev && !p.root_is_leaf)
       CG_CUDA(cudaMemcpyAsync(trace_dev + (size_t)i * p.root_n, p.root_ptr, p.root_n * sizeof(float),
                               cudaMemcpyDeviceToDevice, rt.stream));

@@ -69,6 +69,7 @@ void Runtime::init() {
   if (const char* s = getenv("CG_HOIST")) hoist = atoi(s);
   if (const char* s = getenv("CG_VM_MAX_DIM")) vm_max_dim = atoi(s);
   if (const char* s = getenv("CG_TAPE_JIT")) tape_jit = atoi(s);
+  if (const char* s = getenv("CG_ELIDE_ROOT")) elide_root = atoi(s);
   if (const char* s = getenv("CG_EW_JIT_MIN")) ew_jit_min = atoll(s);
   if (g_plan_only) ew_jit_min = -1;
 }

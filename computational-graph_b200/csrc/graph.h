@@ -82,6 +82,7 @@ struct Runtime {
   long long ew_jit_min = 32768;  // elementwise programs over >= this many elements are specialised (ew_jit.cpp); < 0: never
   int hoist = 1;         // dag mode: move loss-independent backward work next to the forward ops it depends on (plan.cpp)
   int vm_max_dim = 48;   // plans whose every matrix dimension is <= this run on the resident tape executor (vm_kernel.cu); 0: never
+  int elide_root = 1;    // iterations whose root value is unobservable (Q12) skip its store (elementwise-only graphs)
   int tape_jit = 1;      // resident plans are compiled into one shared-memory-resident kernel when they fit (ew_jit.cpp)
   int io_graph = 1;      // put the H2D / D2H transfers of a `minimize(&args, lr, 1)` call inside the iteration graph
   std::vector<cudaStream_t> side_streams;

@@ -99,8 +99,8 @@ void launch_tape_jit(const TapeKernel* k, int iters, float* trace, cudaStream_t 
 
 struct PlanStats {
   size_t tape_instrs = 0, live_instrs = 0, ew_groups = 0, gemms = 0, gemms_fused_sgd = 0, reduces = 0;
-  size_t arena_bytes = 0, kernels_per_iter = 0, ew_specialised = 0, allreduces = 0, dp_fused_updates = 0, vm_resident = 0, tape_smem_bytes = 0;
-  double gemm_flop_per_iter = 0.0, ew_bytes_per_iter = 0.0;
+  size_t arena_bytes = 0, kernels_per_iter = 0, ew_specialised = 0, allreduces = 0, dp_fused_updates = 0, vm_resident = 0, tape_smem_bytes = 0, quiet_variant = 0;
+  double gemm_flop_per_iter = 0.0, ew_bytes_per_iter = 0.0, quiet_ew_bytes_per_iter = 0.0;
 };
 
 // The iteration graph with the host transfers of one `minimize(&args, lr, 1)` call inside it: H2D copies of the
@@ -138,6 +138,9 @@ struct Plan {
   IoGraph io[2];                    // [0] without, [1] with the D2H read of the root value
   std::vector<BufRef> io_staging;   // row-major landing buffer per matrix input
   // resident tape executor (vm_kernel.cu): the steps and programs in device memory, when the plan is small enough
+  // The same iteration without the store of the root value: only the last iteration's value is observable (Q12), and
+  // for an elementwise-only graph (C2) that store is 4 of the 28 bytes per element the fused kernel moves.
+  std::shared_ptr<Plan> quiet;
   const TapeKernel* tape_kernel = nullptr;  // the compiled form (shared-memory resident), preferred when present
   VmStep* vm_steps = nullptr;
   EwProgram* vm_progs = nullptr;
@@ -146,7 +149,7 @@ struct Plan {
   void release_graphs();  // destroy the captured CUDA graphs (they are re-captured on the next use)
 };
 
-std::shared_ptr<Plan> build_plan(Function& root, float lr);
+std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root = true);
 // Destroys the CUDA graphs of every live plan. NCCL keeps a communicator alive while a captured graph still holds one
 // of its collectives (ncclCommDestroy would wait forever), so cg_dp_shutdown calls this first.
 void release_all_plan_graphs();

@@ -108,6 +108,10 @@ void cg_set_vm_max_dim(int dim);
  * (NVRTC) into ONE straight-line kernel — shapes as constants, every leaf and temporary in shared memory for the
  * whole minimize call, leaves loaded once and written back once. 0: the interpreting executor / the CUDA graph. */
 void cg_set_tape_jit(int on);
+/* 1 (default): after minimize(n) only the LAST iteration's root value is observable (src/optimize.rs:64-71) unless it is
+ * traced or printed, so for elementwise-only graphs iterations 1..n-1 run a variant of the fused kernel that does not
+ * store it (C2: 24 instead of 28 bytes per element). Same parameter updates, same final value. 0: always store. */
+void cg_set_elide_root(int on);
 
 /* ---- introspection -------------------------------------------------------------------------------- */
 typedef struct {
@@ -119,6 +123,8 @@ typedef struct {
   unsigned long long dp_fused_updates; /* data parallel: all-reduce + SGD update as one peer-memory kernel */
   unsigned long long vm_resident;      /* resident executor: 0 none (CUDA graph), 1 interpreting (vm_kernel.cu), 2 compiled */
   unsigned long long tape_smem_bytes;  /* compiled resident kernel: shared memory holding every value of the plan */
+  unsigned long long quiet_variant;    /* 1: iterations with an unobservable root value skip its store (cg_set_elide_root) */
+  double quiet_ew_bytes_per_iter;      /* elementwise bytes of such an iteration */
 } cg_plan_stats;
 int cg_plan_stats_get(cg_function *f, float learn_rate, cg_plan_stats *out); /* compiles the plan if needed */
 /* One text line per kernel of the compiled iteration, in launch order ("<i> GEMM m= n= k= ta= tb= epi=", "<i> EW n= in= out=

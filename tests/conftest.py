@@ -42,4 +42,5 @@ def cg():
     api.set_hoist(True)
     api.set_vm_max_dim(48)
     api.set_tape_jit(True)
+    api.set_elide_root(True)
     return api

@@ -208,6 +208,36 @@ def test_resident_executor_is_bit_identical_to_the_graph(cg, case):
             assert np.array_equal(np.asarray(a[2][k]).view(np.int32), np.asarray(b[2][k]).view(np.int32)), k
 
 
+def test_root_store_elision_is_unobservable(cg, oracle):
+    """cg_set_elide_root: iterations whose root value nobody can observe run without storing it. Leaves, the cached
+    root value after the call (Q12: the forward value of the LAST iteration), traces and prints must be what they are
+    with the store in every iteration, and equal to the oracle."""
+    n = 96  # 9216 elements: above the resident executor's limit, so this is the CUDA-graph path
+    res = []
+    for elide in (False, True):
+        cg.set_elide_root(elide)
+        f = c2_graph(cg, n)
+        st = cg.plan_stats(f, 0.01)
+        assert st["vm_resident"] == 0 and st["quiet_variant"] == (1 if elide else 0)
+        if elide:
+            assert st["ew_bytes_per_iter"] == 28 * n * n and st["quiet_ew_bytes_per_iter"] == 24 * n * n
+        f.minimize({}, 0.01, 7)
+        v1 = np.array(f.value())
+        tr = np.array(f.minimize({}, 0.01, 4, trace=True))
+        f.minimize({}, 0.01, 1)
+        v2 = np.array(f.value())
+        res.append((v1, tr, v2, leaves_dict(f)))
+    cg.set_elide_root(True)
+    a, b = res
+    for x, y in zip(a[:3], b[:3]):
+        assert np.array_equal(x.view(np.int32), y.view(np.int32))
+    for k in a[3]:
+        assert np.array_equal(a[3][k].view(np.int32), b[3][k].view(np.int32)), k
+    fo = c2_graph(oracle, n)
+    fo.minimize({}, 0.01, 7)
+    assert rel_err(b[0], np.asarray(fo.value())) < 1e-5
+
+
 def test_medium_lstm_tiled_gemm(cg, oracle):
     """Products above the strict-kernel limit take the tiled FP32 SIMT kernel (FMA accumulation): 1e-5."""
     cg.set_mode("dag")

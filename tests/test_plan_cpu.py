@@ -32,6 +32,9 @@ def test_c1_and_c2_are_one_fused_kernel(plans):
     assert c2["kernels_per_iter"] == 1 and c2["arena_bytes"] == 0
     assert c2["kernels"][0].split()[1] == "EW"
     assert c2["ew_bytes_per_iter"] == 28 * 64 * 64
+    # iterations whose root value is unobservable (Q12) skip its store: exactly SURVEY §8d's 24 bytes per element
+    assert c2["quiet_variant"] == 1 and c2["quiet_ew_bytes_per_iter"] == 24 * 64 * 64
+    assert plans["c4_hoist1"]["quiet_variant"] == 0
 
 
 def test_c3_kernel_counts(plans):

@@ -116,6 +116,60 @@ void capture_nodes(Plan& p, Runtime& rt, std::vector<CapNode>& nodes, cudaGraph_
       l.readers.clear();
     }
   }
+  static const bool exact_dag = [] {
+    const char* e = getenv("CG_GRAPH_EXACT");
+    return !e || atoi(e) != 0;
+  }();
+  if (exact_dag) {
+    // Exact DAG: everything is captured on ONE stream whose capture dependency set is replaced, before every node,
+    // by exactly the nodes that node depends on (cudaStreamUpdateCaptureDependencies). No stream-order edges exist, so
+    // a kernel that waits for a late input can never hold back an unrelated kernel that happened to be captured
+    // behind it on the same stream — with side streams that cost 2.0 ms of a C4 iteration fed from the host.
+    std::vector<std::vector<cudaGraphNode_t>> after(n);  // the dependency set of the stream after node i
+    std::vector<char> has_succ(n, 0);
+    int lane_last[kIoLanes];
+    for (int& l : lane_last) l = -1;
+    CG_CUDA(cudaStreamBeginCapture(rt.stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      for (size_t i = 0; i < n; i++) {
+        std::vector<cudaGraphNode_t> d;
+        auto add_after = [&](int dep) {
+          has_succ[dep] = 1;
+          for (cudaGraphNode_t g : after[dep])
+            if (std::find(d.begin(), d.end(), g) == d.end()) d.push_back(g);
+        };
+        for (int dep : deps[i]) add_after(dep);
+        // lanes stay in order: every rank must issue the exchanges of one communicator in the same order, and the
+        // inputs are copied in the order the iteration needs them
+        const int lane = nodes[i].lane;
+        if (lane >= 0 && lane < kIoLanes && lane_last[lane] >= 0) add_after(lane_last[lane]);
+        CG_CUDA(cudaStreamUpdateCaptureDependencies(rt.stream, d.empty() ? nullptr : d.data(), d.size(), cudaStreamSetCaptureDependencies));
+        nodes[i].launch(rt.stream);
+        cudaStreamCaptureStatus status;
+        const cudaGraphNode_t* cur = nullptr;
+        size_t ncur = 0;
+        CG_CUDA(cudaStreamGetCaptureInfo(rt.stream, &status, nullptr, nullptr, &cur, &ncur));
+        if (status != cudaStreamCaptureStatusActive) throw Error("internal: stream capture was invalidated");
+        after[i].assign(cur, cur + ncur);
+        if (lane >= 0 && lane < kIoLanes) lane_last[lane] = (int)i;
+      }
+      // end on the join of every sink
+      std::vector<cudaGraphNode_t> sinks;
+      for (size_t i = 0; i < n; i++)
+        if (!has_succ[i])
+          for (cudaGraphNode_t g : after[i])
+            if (std::find(sinks.begin(), sinks.end(), g) == sinks.end()) sinks.push_back(g);
+      CG_CUDA(cudaStreamUpdateCaptureDependencies(rt.stream, sinks.empty() ? nullptr : sinks.data(), sinks.size(), cudaStreamSetCaptureDependencies));
+    } catch (...) {
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(rt.stream, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    CG_CUDA(cudaStreamEndCapture(rt.stream, graph_out));
+    CG_CUDA(cudaGraphInstantiate(exec_out, *graph_out, 0));
+    return;
+  }
   // streams: [0] the capturing (origin) stream, [1, nstreams] compute side streams, then the transfer lanes
   std::vector<cudaStream_t> streams{rt.stream};
   for (int k = 0; k < nstreams + kIoLanes; k++) streams.push_back(rt.side_streams[k]);
@@ -215,6 +269,53 @@ bool io_graph_eligible(const Plan& p, const Runtime& rt, const std::vector<Arg>&
   return !trace || is_pinned_host(trace);
 }
 
+// The order in which the inputs of one call should arrive. The walker discovers leaves depth first, which for a
+// recurrence is LAST time-step first (the root is C_T; x_T-1 is met before the walk descends to step 0), but the
+// step that needs x_0 has the whole recurrence behind it. So inputs are ranked by the weight (flop) of the longest
+// dependency chain that starts at one of their consumers: with x_0 copied last, 2.0 of the 2.8 ms of H2D time of a
+// C4 iteration were exposed (11.05 vs 9.02 ms, tools/probes/e2e_timing.py).
+std::vector<size_t> input_urgency_order(Plan& p, const Runtime& rt) {
+  const size_t n = p.steps.size();
+  std::vector<CapNode> nodes;
+  for (size_t i = 0; i < n; i++) nodes.push_back(step_node(p, i, rt));
+  std::unordered_map<const float*, Loc> loc;
+  std::vector<std::vector<int>> succ(n);
+  for (size_t i = 0; i < n; i++) {
+    auto dep = [&](int d) {
+      if (d >= 0 && d != (int)i) succ[d].push_back((int)i);
+    };
+    for (const float* r : nodes[i].reads) dep(loc[r].last_writer);
+    for (const float* w : nodes[i].writes) {
+      Loc& l = loc[w];
+      dep(l.last_writer);
+      for (int rd : l.readers) dep(rd);
+    }
+    for (const float* r : nodes[i].reads) loc[r].readers.push_back((int)i);
+    for (const float* w : nodes[i].writes) {
+      Loc& l = loc[w];
+      l.last_writer = (int)i;
+      l.readers.clear();
+    }
+  }
+  std::vector<double> tail(n, 0.0);
+  for (size_t k = n; k-- > 0;) {
+    double best = 0.0;
+    for (int s : succ[k]) best = std::max(best, tail[s]);
+    tail[k] = best + plan_step_flop(p, k) + 1e6;  // every kernel costs something, products their flop
+  }
+  const size_t nin = p.input_leaves.size();
+  std::vector<double> urgency(nin, 0.0);
+  for (size_t j = 0; j < nin; j++) {
+    const float* buf = p.input_leaves[j]->value.buf->ptr;
+    for (size_t i = 0; i < n; i++)
+      if (std::find(nodes[i].reads.begin(), nodes[i].reads.end(), buf) != nodes[i].reads.end()) urgency[j] = std::max(urgency[j], tail[i]);
+  }
+  std::vector<size_t> order(nin);
+  for (size_t j = 0; j < nin; j++) order[j] = j;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return urgency[a] > urgency[b]; });
+  return order;
+}
+
 void launch_io_graph(Plan& p, Runtime& rt, const std::vector<Arg>& args, float* trace) {
   IoGraph& g = p.io[trace ? 1 : 0];
   const size_t nin = p.input_leaves.size();
@@ -227,6 +328,18 @@ void launch_io_graph(Plan& p, Runtime& rt, const std::vector<Arg>& args, float* 
     g.h2d_dst.assign(nin, nullptr);
     g.h2d_bytes.assign(nin, 0);
     g.d2h_dst = trace;
+    // H2D memcpy nodes inside a multi-branch graph cost ~1.3 ms per C4 iteration over the same copies overlapped by
+    // hand (11.1 vs 9.85 ms on B200; tools/e2e_probe.py): by default the copies run on a copy stream of their own and
+    // the graph holds an external-event wait per input. CG_IO_EXTERNAL=0 keeps them as memcpy nodes.
+    static const bool external = [] {
+      const char* e = getenv("CG_IO_EXTERNAL");
+      return !e || atoi(e) != 0;
+    }();
+    g.external_h2d = external;
+    if (external) {
+      g.in_ev.resize(nin);
+      for (auto& e : g.in_ev) CG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     std::vector<CapNode> nodes;
     IoGraph* gp = &g;
     Plan* pp = &p;
@@ -242,7 +355,8 @@ void launch_io_graph(Plan& p, Runtime& rt, const std::vector<Arg>& args, float* 
     };
     // a leaf root is read BEFORE this iteration's update overwrites it (Q12)
     if (trace && p.root_is_leaf) nodes.push_back(d2h());
-    for (size_t i = 0; i < nin; i++) {
+    g.order = input_urgency_order(p, rt);
+    for (size_t i : g.order) {
       Value& v = p.input_leaves[i]->value;
       const size_t n = v.size();
       const bool direct = !v.is_matrix || v.h == 1 || v.w == 1;  // both layouts coincide
@@ -252,10 +366,15 @@ void launch_io_graph(Plan& p, Runtime& rt, const std::vector<Arg>& args, float* 
       CapNode c;
       c.lane = 0;  // one copy-in lane: the inputs arrive in the order the forward pass consumes them
       c.writes.push_back(g.h2d_dst[i]);
-      c.launch = [gp, i](cudaStream_t st) {
-        CG_CUDA(cudaMemcpyAsync(gp->h2d_dst[i], gp->h2d_src[i], gp->h2d_bytes[i], cudaMemcpyHostToDevice, st));
-        gp->h2d_nodes[i] = last_captured_node(st);
-      };
+      if (g.external_h2d) {
+        // the copy itself is enqueued on the copy stream before every launch; the graph only waits for it
+        c.launch = [gp, i](cudaStream_t st) { CG_CUDA(cudaStreamWaitEvent(st, gp->in_ev[i], cudaEventWaitExternal)); };
+      } else {
+        c.launch = [gp, i](cudaStream_t st) {
+          CG_CUDA(cudaMemcpyAsync(gp->h2d_dst[i], gp->h2d_src[i], gp->h2d_bytes[i], cudaMemcpyHostToDevice, st));
+          gp->h2d_nodes[i] = last_captured_node(st);
+        };
+      }
       nodes.push_back(std::move(c));
       if (!direct) {
         CapNode t;
@@ -273,17 +392,46 @@ void launch_io_graph(Plan& p, Runtime& rt, const std::vector<Arg>& args, float* 
     for (size_t i = 0; i < p.steps.size(); i++) nodes.push_back(step_node(p, i, rt));
     if (trace && !p.root_is_leaf) nodes.push_back(d2h());
     capture_nodes(p, rt, nodes, &g.graph, &g.exec);
-  } else {
+  } else if (!g.external_h2d) {
     for (size_t i = 0; i < nin; i++)
       if (g.h2d_src[i] != src[i]) {
         CG_CUDA(cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.h2d_nodes[i], g.h2d_dst[i], src[i], g.h2d_bytes[i],
                                                    cudaMemcpyHostToDevice));
         g.h2d_src[i] = src[i];
       }
-    if (trace && g.d2h_dst != trace) {
-      CG_CUDA(cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.d2h_node, trace, p.root_ptr, p.root_n * sizeof(float),
-                                                 cudaMemcpyDeviceToHost));
-      g.d2h_dst = trace;
+  }
+  if (g.exec && trace && g.d2h_dst != trace) {
+    CG_CUDA(cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.d2h_node, trace, p.root_ptr, p.root_n * sizeof(float),
+                                               cudaMemcpyDeviceToHost));
+    g.d2h_dst = trace;
+  }
+  if (g.external_h2d) {
+    // this call's copies, in consumption order, behind everything that still reads the landing buffers
+    cudaStream_t copy = rt.side_streams[(size_t)(rt.graph_streams > 0 ? rt.graph_streams : 0) + 0];
+    if (!p.io_done) CG_CUDA(cudaEventCreateWithFlags(&p.io_done, cudaEventDisableTiming));
+    CG_CUDA(cudaEventRecord(p.io_done, rt.stream));
+    CG_CUDA(cudaStreamWaitEvent(copy, p.io_done, 0));
+    static const bool dbg = getenv("CG_DEBUG_TIMING") != nullptr;
+    static const bool skip = getenv("CG_IO_SKIP_COPY") != nullptr;  // bring-up probe: pretend the inputs have landed
+    static cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (dbg && !t0) {
+      cudaEventCreate(&t0);
+      cudaEventCreate(&t1);
+    }
+    if (dbg) cudaEventRecord(t0, copy);
+    for (size_t i : g.order) {
+      if (!skip) CG_CUDA(cudaMemcpyAsync(g.h2d_dst[i], src[i], g.h2d_bytes[i], cudaMemcpyHostToDevice, copy));
+      CG_CUDA(cudaEventRecord(g.in_ev[i], copy));
+    }
+    if (dbg) {
+      cudaEventRecord(t1, copy);
+      CG_CUDA(cudaGraphLaunch(g.exec, rt.stream));
+      rt.launches += p.steps.size() + g.layout_kernels;
+      cudaEventSynchronize(t1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t0, t1);
+      fprintf(stderr, "[cg timing] copy stream: %zu H2D copies took %.3f ms next to the iteration\n", nin, ms);
+      return;
     }
   }
   CG_CUDA(cudaGraphLaunch(g.exec, rt.stream));

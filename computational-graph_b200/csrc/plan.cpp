@@ -23,6 +23,7 @@ Plan::~Plan() {
   if (vm_progs) cudaFree(vm_progs);
   release_graphs();
   for (cudaEvent_t e : events) cudaEventDestroy(e);
+  if (io_done) cudaEventDestroy(io_done);
 }
 
 void Plan::release_graphs() {
@@ -33,6 +34,7 @@ void Plan::release_graphs() {
   for (IoGraph& g : io) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
     if (g.graph) cudaGraphDestroy(g.graph);
+    for (cudaEvent_t e : g.in_ev) cudaEventDestroy(e);  // after the graph whose wait nodes name them
     g = IoGraph();
   }
 }

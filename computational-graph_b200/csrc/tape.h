@@ -116,6 +116,11 @@ struct IoGraph {
   cudaGraphNode_t d2h_node = nullptr;
   float* d2h_dst = nullptr;
   size_t layout_kernels = 0;
+  // External-copy form (default): the H2D copies are enqueued on a copy stream right before the graph launch and the
+  // graph holds one event-wait node per input instead of a memcpy node (exec.cpp launch_io_graph).
+  std::vector<size_t> order;  // input indices, most urgent first (longest chain of work behind their first consumer)
+  bool external_h2d = false;
+  std::vector<cudaEvent_t> in_ev;  // one per input leaf: "this call's copy of input i has landed"
 };
 
 struct Plan {
@@ -137,6 +142,7 @@ struct Plan {
   std::vector<cudaEvent_t> events;  // one per captured node (+1 fork event) for the multi-stream capture
   IoGraph io[2];                    // [0] without, [1] with the D2H read of the root value
   std::vector<BufRef> io_staging;   // row-major landing buffer per matrix input
+  cudaEvent_t io_done = nullptr;    // recorded behind every transfer-graph launch: the staging buffers are free again
   // resident tape executor (vm_kernel.cu): the steps and programs in device memory, when the plan is small enough
   // The same iteration without the store of the root value: only the last iteration's value is observable (Q12), and
   // for an elementwise-only graph (C2) that store is 4 of the 28 bytes per element the fused kernel moves.

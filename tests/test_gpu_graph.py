@@ -238,6 +238,36 @@ def test_root_store_elision_is_unobservable(cg, oracle):
     assert rel_err(b[0], np.asarray(fo.value())) < 1e-5
 
 
+@pytest.mark.parametrize("mode", ["exact", "dag"])
+def test_corrected_activation_gradients_match_the_oracle(cg, oracle, mode):
+    """with cg_set_fix_act_grad(1) Sigmoid / Tanh pass error * derivative to their child (the true
+    chain rule instead of Q3). Same switch on the oracle (whose corrected rule is checked against finite differences in
+    tests/test_oracle.py); the LSTM then trains through its gates, and both sides must still agree to 1e-5."""
+    cg.set_mode(mode)
+    oracle.set_mode(mode)
+    cg.set_fix_act_grad(True)
+    oracle.lib.orc_set_fix_act_grad(1)
+    try:
+        fg, fo = readme_lstm(cg, 8, T=2, seed=5), readme_lstm(oracle, 8, T=2, seed=5)
+        tg = fg.minimize({}, 0.01, 8, trace=True)
+        to = fo.minimize({}, 0.01, 8, trace=True)
+        assert rel_err(tg, to) < 1e-5
+        lg, lo = leaves_dict(fg), leaves_dict(fo)
+        for k in lg:
+            assert rel_err(lg[k], lo[k]) < 1e-5, k
+        # and the corrected rule is a different computation from the reference's (Q3)
+        cg.set_fix_act_grad(False)
+        fq = readme_lstm(cg, 8, T=2, seed=5)
+        fq.minimize({}, 0.01, 8)
+        lq = leaves_dict(fq)
+        assert any(rel_err(lq[k], lg[k]) > 1e-3 for k in lg)
+    finally:
+        cg.set_fix_act_grad(False)
+        oracle.lib.orc_set_fix_act_grad(0)
+        oracle.set_mode("exact")
+        cg.set_mode("exact")
+
+
 def test_medium_lstm_tiled_gemm(cg, oracle):
     """Products above the strict-kernel limit take the tiled FP32 SIMT kernel (FMA accumulation): 1e-5."""
     cg.set_mode("dag")

@@ -212,3 +212,54 @@ def test_dag_equals_exact_without_shared_nodes(oracle):
     assert np.array_equal(bits(out[0][0]), bits(out[1][0]))
     for k in out[0][1]:
         assert np.array_equal(bits(out[0][1][k]), bits(out[1][1][k]))
+
+
+def _activation_chain(api, xv, wv, bv, tv):
+    F = api.Function
+    x, t = F.constant(api.Constant(xv)), F.constant(api.Constant(tv))
+    w, b = F.param("W", api.Constant(wv)), F.param("b", api.Constant(bv))
+    return ((api.dot(x, w) + b).sigmoid().tanh() - t).sq()
+
+
+def test_corrected_activation_gradients_match_finite_differences(oracle):
+    """SURVEY §8 row f2. The reference's Sigmoid / Tanh backward rules hand the child the LOCAL derivative and drop
+    the upstream error (Q3, src/optimize.rs:168-179) — reproduced by default because it is the reference's semantics.
+    With the correction switched on (fix_act_grad) the update of every parameter must be -lr * dL/dtheta for
+    L = sum of the root's elements (root error == 1, optimize.rs:69), checked here against central finite differences
+    of the oracle's own forward pass; with the reference rule it must NOT be (that is what Q3 means)."""
+    rng = np.random.default_rng(8)
+    xv = rng.uniform(-1, 1, (4, 3)).astype(np.float32)
+    wv = rng.uniform(-1, 1, (3, 5)).astype(np.float32)
+    bv = rng.uniform(-1, 1, (4, 5)).astype(np.float32)
+    tv = rng.uniform(-1, 1, (4, 5)).astype(np.float32)
+    lr, eps = 1e-2, 1e-2
+
+    def loss(w, b):
+        f = _activation_chain(oracle, xv, w, b, tv)
+        return float(np.asarray(f.minimize({}, 0.0, 1, trace=True), dtype=np.float64).sum())
+
+    def numeric(which):
+        base = {"W": wv, "b": bv}[which]
+        g = np.zeros(base.shape)
+        for idx in np.ndindex(base.shape):
+            hi, lo = base.copy(), base.copy()
+            hi[idx] += eps
+            lo[idx] -= eps
+            g[idx] = ((loss(hi, bv) if which == "W" else loss(wv, hi)) - (loss(lo, bv) if which == "W" else loss(wv, lo))) / (2 * eps)
+        return g
+
+    want = {"W": numeric("W"), "b": numeric("b")}
+    got = {}
+    for fix in (1, 0):
+        oracle.lib.orc_set_fix_act_grad(fix)
+        try:
+            f = _activation_chain(oracle, xv, wv, bv, tv)
+            f.minimize({}, lr, 1)
+            leaves = dict(f.leaves())
+            got[fix] = {"W": (wv.astype(np.float64) - leaves["W"]) / lr, "b": (bv.astype(np.float64) - leaves["b"]) / lr}
+        finally:
+            oracle.lib.orc_set_fix_act_grad(0)
+    for k in ("W", "b"):
+        scale = np.max(np.abs(want[k]))
+        assert np.max(np.abs(got[1][k] - want[k])) < 2e-2 * scale, k      # corrected rule: the true gradient
+        assert np.max(np.abs(got[0][k] - want[k])) > 0.3 * scale, k       # reference rule (Q3): not a gradient

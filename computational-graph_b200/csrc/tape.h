@@ -95,6 +95,7 @@ struct Plan;
 const TapeKernel* tape_jit_build(const Plan& p, bool load);
 void tape_jit_free(const TapeKernel* k);
 size_t tape_jit_smem_bytes(const TapeKernel* k);
+size_t tape_jit_cache_size();  // distinct compiled modules (structurally identical plans share one)
 void launch_tape_jit(const TapeKernel* k, int iters, float* trace, cudaStream_t stream);
 
 struct PlanStats {

@@ -71,3 +71,21 @@ def test_elementwise_specialiser_compiles_for_sm_100a_without_a_gpu(lib):
     lib.cg_last_error.restype = C.c_char_p
     size = lib.cg_ew_jit_selftest()
     assert size > 1000, lib.cg_last_error()
+
+
+def test_rust_shim_binds_only_exported_symbols(lib):
+    """rust_shim/src/ffi.rs (the reference's Rust surface over the graph-level ABI) cannot be compiled
+    in this image; what can be checked is that every `cg_*` function it declares is declared in include/cg_graph.h
+    with the same number of parameters and exported by the library."""
+    ffi = open(os.path.join(ROOT, "rust_shim", "src", "ffi.rs")).read()
+    header = open(os.path.join(ROOT, "include", "cg_graph.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    decls = re.findall(r"pub fn (cg_\w+)\s*\((.*?)\)", ffi, flags=re.S)
+    assert len(decls) >= 25
+    for name, params in decls:
+        assert hasattr(lib, name), name
+        m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", header, flags=re.S)
+        assert m, f"{name} is not declared in cg_graph.h"
+        c_params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        rust_params = [p for p in params.split(",") if p.strip()]
+        assert len(c_params) == len(rust_params), (name, c_params, rust_params)

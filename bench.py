@@ -5,7 +5,9 @@
 
 One "step" = one pass of the `minimize` loop body (src/optimize.rs:64-71) over the BASELINE config-4 LSTM
 (H = I = 4096, T = 8, batch 1024 rows per GPU, f32, dag mode). N > 1 shards the batch rows over the ranks
-(weak scaling: 1024 rows per GPU) with an NCCL sum-allreduce of every weight gradient.
+(weak scaling: 1024 rows per GPU); every weight gradient is summed over the ranks before its update by the fused
+exchange kernel over NVLink peer memory (ncclAllReduce when peer access is unavailable or CG_DP_FUSED=0).
+`--config c5` selects BASELINE config 5 instead (T = 32, global batch 8192 sharded over the ranks, strong scaling).
 
   value    : iterations/sec with every input resident in HBM, CUDA events on the library stream, max over ranks
   e2e      : the same metric through the public call `f.minimize(&args, lr, 1)` (C ABI cg_minimize) with HOST
@@ -34,11 +36,27 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 H = I = 4096
 T = 8
 B_PER_GPU = 1024
+CONFIG = "c4"   # "c4": BASELINE config 4, weak scaling (1024 rows per GPU); "c5": BASELINE config 5 (T = 32, global batch
+                # 8192 sharded over the ranks), strong scaling — select with --config
+GLOBAL_BATCH_C5 = 8192
 LR = 0.01
 SEED = 4
 # (46 (T-1) + 30) B H^2 flop per iteration in dag mode with the dead dX of the constant inputs skipped
 FLOP_PER_ITER_PER_GPU = (46 * (T - 1) + 30) * B_PER_GPU * H * H
 SAMPLE_D = 256  # CPU sample: square LSTM (the reference gemm only accepts equal square operands, Q7)
+
+
+def configure(name: str, world: int) -> None:
+    """Sets the module-level workload constants for the chosen BASELINE config."""
+    global CONFIG, T, B_PER_GPU, FLOP_PER_ITER_PER_GPU
+    CONFIG = name
+    if name == "c5":
+        if GLOBAL_BATCH_C5 % world:
+            raise SystemExit(f"config 5: the global batch of {GLOBAL_BATCH_C5} rows does not divide over {world} ranks")
+        T, B_PER_GPU = 32, GLOBAL_BATCH_C5 // world
+    else:
+        T, B_PER_GPU = 8, 1024
+    FLOP_PER_ITER_PER_GPU = (46 * (T - 1) + 30) * B_PER_GPU * H * H
 
 
 def peaks():
@@ -211,7 +229,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "LSTM fwd+backprop+SGD iterations/sec", "value": scaled, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1000.0 / scaled, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if CONFIG == "c5" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus, "f32"),
         "cpu_baseline": {"value": scaled, "unit": "iterations/s", "cores": 1, "kind": kind, "sample": desc},
         "e2e": {"value": scaled, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,11 +238,15 @@ def run_reference(args):
 
 
 def workload_config(n_gpus, product):
-    return {"workload": f"BASELINE config 4: LSTM H=I={H}, T={T}, batch {B_PER_GPU} rows per GPU (global batch "
+    num = "5" if CONFIG == "c5" else "4"
+    aggregate = ("value = global iterations/s: the 8192-row batch is sharded over the ranks, one step is one iteration "
+                 "of the whole batch (strong scaling)" if CONFIG == "c5" else
+                 "value = n_gpus x (global iterations/s): each GPU runs the 1024-row LSTM iteration of its batch shard")
+    return {"workload": f"BASELINE config {num}: LSTM H=I={H}, T={T}, batch {B_PER_GPU} rows per GPU (global batch "
                         f"{B_PER_GPU * n_gpus}), f32 params, (lstm(inputs)-target).sq(), lr={LR}, dag mode",
             "product": product, "params_13H2": 13 * H * H, "global_batch": B_PER_GPU * n_gpus, "seq_len": T,
             "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
-            "aggregate": "value = n_gpus x (global iterations/s): each GPU runs the 1024-row LSTM iteration of its batch shard",
+            "aggregate": aggregate,
             "l2": "per-iteration working set (>8 GB) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -235,10 +257,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--product", default=os.environ.get("CG_BENCH_PRODUCT", "tf32"), choices=["tf32", "f32"])
+    ap.add_argument("--config", default=os.environ.get("CG_BENCH_CONFIG", "c4"), choices=["c4", "c5"],
+                    help="c4 (default): BASELINE config 4, weak scaling; c5: BASELINE config 5, T=32, global batch 8192, strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-configs", action="store_true",
                     help="with --impl reference: time the reference CPU path on the secondary configs C1-C3 instead")
     args = ap.parse_args()
+    configure(args.config, int(os.environ.get("WORLD_SIZE", "1")) if args.impl == "ours" else max(args.gpus, 1))
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -322,15 +347,16 @@ def main():
         peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
         peak_note = f"FP32 FMA pipe: 148 SMs x 128 lanes x 2 flop x {pk['sm_max_mhz']} MHz (nominal; not in MEASURED_PEAKS.json)"
     achieved = gflop.value / (gms.value * 1e-3) / 1e12 if gms.value > 0 else 0.0
+    agg = 1 if CONFIG == "c5" else world  # config 5: one step = one iteration of the whole (sharded) batch
     total_ms = sum(kind_ms)
     line = {
         # whole-job aggregate: every rank completes one 1024-row LSTM iteration per step (weak scaling), so the job
         # processes `world` shard-iterations per step; at N = 1 this is plain iterations/s
-        "metric": "LSTM fwd+backprop+SGD iterations/sec", "value": world * 1000.0 / ms, "unit": "iterations/s",
+        "metric": "LSTM fwd+backprop+SGD iterations/sec", "value": agg * 1000.0 / ms, "unit": "iterations/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.product, "data": "synthetic",
+        "scaling": "strong" if CONFIG == "c5" else "weak", "vs_baseline": None, "dtype": args.product, "data": "synthetic",
         "config": workload_config(world, args.product),
-        "e2e": {"value": world * 1000.0 / e2e_ms, "unit": "iterations/s", "ms_per_step": e2e_ms,
+        "e2e": {"value": agg * 1000.0 / e2e_ms, "unit": "iterations/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -66,6 +66,10 @@ class ProductApi(Api):
         lib.cg_dp_init.restype, lib.cg_dp_init.argtypes = C.c_int, [C.c_int, C.c_int, C.c_char_p]
         lib.cg_dp_shutdown.restype = C.c_int
         lib.cg_dp_fused.restype = C.c_int
+        lib.cg_grad.restype, lib.cg_grad.argtypes = C.c_void_p, [C.c_void_p, C.c_char_p]
+        lib.cg_eval.restype = C.c_int
+        lib.cg_eval.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(C.c_float)),
+                                C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_float)]
         lib.cg_set_ew_jit_min.restype, lib.cg_set_ew_jit_min.argtypes = None, [C.c_longlong]
         lib.cg_ew_jit_selftest.restype = C.c_longlong
         lib.cg_host_alloc.restype, lib.cg_host_alloc.argtypes = C.c_void_p, [C.c_size_t]
@@ -149,6 +153,30 @@ class ProductApi(Api):
 
     def minimize_async(self, f, learn_rate: float, iters: int):
         self._check(self.lib.cg_minimize_async(f._h, float(learn_rate), int(iters)))
+
+    # optimize.rs:8-56 ---------------------------------------------------------------------------
+    def grad(self, f, param: str):
+        """`f.grad(param)`: a new Function, d f / d param, built symbolically (the README's "naive" gradient)."""
+        return self._wrap(self.lib.cg_grad(f._h, param.encode()))
+
+    def eval(self, f, args=None):
+        """`f.eval(&args)`: the forward value at the current parameters; nothing cached changes."""
+        args = args or {}
+        n = len(args)
+        names = (C.c_char_p * max(n, 1))()
+        ptrs = (C.POINTER(C.c_float) * max(n, 1))()
+        hs, ws = (C.c_uint * max(n, 1))(), (C.c_uint * max(n, 1))()
+        keep = []
+        for i, (k, v) in enumerate(args.items()):
+            names[i] = k.encode()
+            arr = np.ascontiguousarray(np.atleast_1d(np.asarray(v.value, dtype=np.float32)))
+            keep.append(arr)
+            ptrs[i] = arr.ctypes.data_as(C.POINTER(C.c_float))
+            hs[i], ws[i] = (v.value.shape if v.is_matrix else (0, 0))
+        d = f.dims()
+        out = np.zeros(d[0] * d[1] if d else 1, dtype=np.float32)
+        self._check(self.lib.cg_eval(f._h, n, names, ptrs, hs, ws, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out.reshape(d[1], d[0]).T.copy() if d else np.float32(out[0])
 
     # data parallel ------------------------------------------------------------------------------
     def dp_unique_id(self) -> bytes:

@@ -246,6 +246,15 @@ class Function:
     def _bin(self, name: str, other: "Function") -> "Function":
         return self._api._wrap(self._api._sym(name)(self._h, other._h))
 
+    # optimize.rs:8-56 (bound by the product only; the CPU oracle restates the hot loop, not these)
+    def grad(self, param: str) -> "Function":
+        """`f.grad(param)`: a new Function, d f / d param, built symbolically."""
+        return self._api.grad(self, param)
+
+    def eval(self, args=None):
+        """`f.eval(&args)`: the forward value at the current parameters."""
+        return self._api.eval(self, args)
+
     def sq(self): return self._un("sq")
     def abs(self): return self._un("abs")
     def signum(self): return self._un("signum")

@@ -100,6 +100,16 @@ int cg_maximize(cg_function* f, int nargs, const char** names, const float** arg
     minimize(*n, pack_args(nargs, names, arg_vals, arg_h, arg_w), lr, iters, print_freq, trace, true);
   });
 }
+// optimize.rs:8-56: forward evaluation and the symbolic ("naive") gradient
+int cg_eval(cg_function* f, int nargs, const char** names, const float** arg_vals, const unsigned* arg_h, const unsigned* arg_w,
+            float* dst) {
+  return guard_rc([&] { function_eval(*F(f), pack_args(nargs, names, arg_vals, arg_h, arg_w), dst); });
+}
+cg_function* cg_grad(const cg_function* f, const char* param) {
+  cg_function* out = nullptr;
+  guard_rc([&] { out = reinterpret_cast<cg_function*>(function_grad(*F(f), param ? param : "")); });
+  return out;
+}
 void* cg_host_alloc(size_t bytes) {
   void* ptr = nullptr;
   guard_rc([&] {

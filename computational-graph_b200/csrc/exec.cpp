@@ -440,6 +440,24 @@ void launch_io_graph(Plan& p, Runtime& rt, const std::vector<Arg>& args, float* 
 
 }  // namespace
 
+// `f.eval(&args)` (optimize.rs:8-32): one forward pass, no parameter is touched and the cached value of `f` stays what
+// it was. The forward-only tape is compiled once per function and launched eagerly (eval is not a loop).
+void function_eval(Function& f, const std::vector<Arg>& args, float* dst) {
+  if (plan_only()) throw Error("plan-only mode: eval needs a CUDA device (this backend has no CPU path)");
+  Runtime& rt = Runtime::get();
+  if (!f.eval_plan || f.eval_plan->mode != rt.mode || f.eval_plan->tf32 != rt.tf32 || f.eval_plan->fuse != rt.fuse ||
+      f.eval_plan->dp_epoch != rt.dp_epoch || f.eval_plan->ew_jit_min != rt.ew_jit_min) {
+    f.eval_plan.reset();
+    f.eval_plan = build_plan(f, 0.0f, /*keep_root=*/true, /*forward_only=*/true);
+  }
+  Plan& p = *f.eval_plan;
+  upload_inputs(p, args);
+  plan_launch_iteration(p, rt.stream);
+  rt.launches += p.steps.size();
+  CG_CUDA(cudaMemcpyAsync(dst, p.root_ptr, p.root_n * sizeof(float), cudaMemcpyDeviceToHost, rt.stream));
+  CG_CUDA(cudaStreamSynchronize(rt.stream));
+}
+
 // Captures the iteration of `p` as a CUDA graph (a DAG over side streams, or one linear stream) if it is not yet.
 static void ensure_graph(Plan& p, Runtime& rt) {
   if (!rt.use_graph || p.graph_exec || p.steps.empty()) return;

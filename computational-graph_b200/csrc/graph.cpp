@@ -317,6 +317,56 @@ static Function* fold_constant(Function* g) {
   return c;
 }
 
+// ---- symbolic gradient (optimize.rs:34-56): the README's "naive" way of getting gradients ------------------------
+// `f.grad(param)` builds a new Function for df/dparam out of the ordinary constructors (so the reference's
+// construction-time rules — identity elimination, constant folding — apply to it as well). The reference's Sq rule,
+// `&f.grad(param) * f`, drops the factor 2 (optimize.rs:38); this is the mathematics: d(f^2) = 2 f f'.
+static bool mentions(const Function& f, const std::string& name, std::unordered_set<const Expr*>& seen) {
+  const Expr& e = *f.body;
+  if (e.kind == Kind::Param || e.kind == Kind::Input) return e.name == name;  // function.rs:105-112: both name a "param"
+  if (e.kind == Kind::Constant) return false;
+  if (!seen.insert(&e).second) return false;  // already searched through another path
+  return (e.f1 && mentions(*e.f1, name, seen)) || (e.f2 && mentions(*e.f2, name, seen));
+}
+
+Function* function_grad(const Function& f, const std::string& param) {
+  typedef std::unique_ptr<Function> P;
+  {
+    std::unordered_set<const Expr*> seen;
+    if (!mentions(f, param, seen)) return make_scalar_leaf(Kind::Constant, nullptr, 0.0f);  // optimize.rs:53-55
+  }
+  const Expr& e = *f.body;
+  auto G = [&](const Function& c) { return P(function_grad(c, param)); };
+  auto un = [](Kind k, const Function& a) { return P(make_unary(k, a)); };
+  auto bin = [](Kind k, const Function& a, const Function& b) { return P(make_binary(k, a, b)); };
+  switch (e.kind) {
+    case Kind::Neg: return make_unary(Kind::Neg, *G(*e.f1));
+    case Kind::Sq: {
+      P two(make_scalar_leaf(Kind::Constant, nullptr, 2.0f));
+      return make_binary(Kind::Mul, *bin(Kind::Mul, *two, *G(*e.f1)), *e.f1);
+    }
+    case Kind::Abs: return make_binary(Kind::Mul, *un(Kind::Signum, *e.f1), *G(*e.f1));  // :39
+    case Kind::Signum: throw Error("signum is nondifferentiable");                        // :40
+    case Kind::Sigmoid: {                                                                 // :41-42: f' * (s * (1 - s))
+      P one(make_scalar_leaf(Kind::Constant, nullptr, 1.0f));
+      return make_binary(Kind::Mul, *G(*e.f1), *bin(Kind::Mul, f, *bin(Kind::Sub, *one, f)));
+    }
+    case Kind::Tanh: {                                                                    // :43-44: f' * (1 - t^2)
+      P one(make_scalar_leaf(Kind::Constant, nullptr, 1.0f));
+      return make_binary(Kind::Mul, *G(*e.f1), *bin(Kind::Sub, *one, *un(Kind::Sq, f)));
+    }
+    case Kind::Add: return make_binary(Kind::Add, *G(*e.f1), *G(*e.f2));
+    case Kind::Sub: return make_binary(Kind::Sub, *G(*e.f1), *G(*e.f2));
+    case Kind::Mul:                                                                       // :47-48
+      return make_binary(Kind::Add, *bin(Kind::Mul, *G(*e.f1), *e.f2), *bin(Kind::Mul, *G(*e.f2), *e.f1));
+    case Kind::Dot: throw Error("not implemented");                                       // :49
+    case Kind::Param:                                                                     // :50-51: ones like the value
+      return f.value.is_matrix ? make_fill_leaf(Kind::Constant, nullptr, f.value.h, f.value.w, 1.0f)
+                               : make_scalar_leaf(Kind::Constant, nullptr, 1.0f);
+    default: throw Error("should never reach here");                                      // :52 (an Input named `param`)
+  }
+}
+
 // Param leaves in memoised post-order (children f1 then f2); every use site is its own leaf (Q1).
 static void collect(Function& f, std::unordered_set<const Expr*>& seen, std::vector<Function*>& out) {
   Expr& e = *f.body;

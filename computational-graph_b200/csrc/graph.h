@@ -55,6 +55,7 @@ struct Function {
   bool has_params = false;  // !params.is_empty() (function.rs:12; Input names count, function.rs:107)
   std::shared_ptr<Expr> body;
   std::shared_ptr<Plan> plan;  // compiled tape, cached on the root the user optimises
+  std::shared_ptr<Plan> eval_plan;  // forward-only tape of `eval` (optimize.rs:8-32)
   int plan_mode = -1;
 };
 
@@ -123,5 +124,8 @@ struct Arg {
 void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, int print_freq, float* trace,
               bool synchronize, bool reuse_inputs = false);
 std::vector<Function*> collect_param_leaves(Function& root);
+// optimize.rs:8-56
+Function* function_grad(const Function& f, const std::string& param);        // symbolic df/dparam
+void function_eval(Function& f, const std::vector<Arg>& args, float* dst);   // forward value, storage order; no cached state changes
 
 }  // namespace cg

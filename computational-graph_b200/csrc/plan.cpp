@@ -943,7 +943,7 @@ void bind_dp_updates(Plan& p) {
 
 void build_vm(Plan& p);
 
-std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root) {
+std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root, bool forward_only) {
   Runtime& rt = Runtime::get();
   auto plan = std::make_shared<Plan>();
   plan_registry().push_back(plan);
@@ -965,6 +965,13 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root) {
   if (is_leaf(root.body->kind)) {
     p.root_is_leaf = true;
     p.root_ptr = root.value.buf->ptr;
+  } else if (forward_only) {
+    // `eval` returns a fresh Constant and leaves the cached value alone (optimize.rs:8-32): a buffer of the plan's own
+    p.eval_root = DevBuf::alloc(rsh.n());
+    p.vals[root_val].fixed = p.eval_root->ptr;
+    p.vals[root_val].keep = p.eval_root;
+    p.vals[root_val].persistent = true;
+    p.root_ptr = p.eval_root->ptr;
   } else if (keep_root) {
     // the root's cached value must survive the iteration (Q12; print / all_less_than / value readback)
     if (!root.value.buf || root.value.buf->n != rsh.n()) root.value.buf = DevBuf::alloc(rsh.n());
@@ -975,9 +982,11 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root) {
   }
   const size_t n_forward = p.tape.size();
   // optimize.rs:69 — `let mut error = self.value_mut().copy_and_fill(1.)`
-  int error = b.emit(IOp::Fill, rsh, -1, -1, 1.0f);
-  if (p.mode == 0) b.backprop_tree(root, error);
-  else b.backprop_dag(root, error);
+  if (!forward_only) {
+    int error = b.emit(IOp::Fill, rsh, -1, -1, 1.0f);
+    if (p.mode == 0) b.backprop_tree(root, error);
+    else b.backprop_dag(root, error);
+  }
 
   p.stats.tape_instrs = p.tape.size();
   dead_code_elimination(p);
@@ -992,7 +1001,7 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root) {
   assign_memory(p);
   finalize_steps(p);
   bind_dp_updates(p);
-  if (!keep_root) return plan;
+  if (!keep_root || forward_only) return plan;
   build_vm(p);
   // Elementwise-only graphs whose root store is a visible share of the traffic get a second, "quiet" plan for the
   // iterations whose root value nobody can observe (exec.cpp).

@@ -129,6 +129,7 @@ struct Plan {
   std::vector<Instr> tape;
   std::vector<Step> steps;
   BufRef arena;
+  BufRef eval_root;  // forward-only plans (`eval`): the root value, in a buffer of the plan's own
   PlanStats stats;
   float lr = 0.0f;
   int mode = 0, tf32 = 0, fix_act_grad = 0, fuse = 1, dp_epoch = 0, hoist = 0;
@@ -156,7 +157,7 @@ struct Plan {
   void release_graphs();  // destroy the captured CUDA graphs (they are re-captured on the next use)
 };
 
-std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root = true);
+std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root = true, bool forward_only = false);
 // Destroys the CUDA graphs of every live plan. NCCL keeps a communicator alive while a captured graph still holds one
 // of its collectives (ncclCommDestroy would wait forever), so cg_dp_shutdown calls this first.
 void release_all_plan_graphs();

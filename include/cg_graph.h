@@ -70,6 +70,13 @@ int cg_minimize_async(cg_function *f, float learn_rate, int iters);
 int cg_synchronize(void);
 
 /* ---- read-back: Function::value / all_less_than / all_equal (src/ops.rs:309-329) ----------------- */
+/* `f.eval(&args)` (src/optimize.rs:8-32): the forward value of f at the current parameters, written to dst in storage
+ * (column-major) order — cg_value_dims gives the shape. No parameter and no cached value changes. */
+int cg_eval(cg_function *f, int nargs, const char **names, const float **arg_vals, const unsigned *arg_h,
+            const unsigned *arg_w, float *dst);
+/* `f.grad(param)` (src/optimize.rs:34-56): a NEW function, d f / d param, built symbolically (the README's "naive"
+ * gradient; products are "not implemented", as in the reference). d(f^2) = 2 f f' — the reference drops the 2. */
+cg_function *cg_grad(const cg_function *f, const char *param);
 int cg_value_dims(const cg_function *f, unsigned *h, unsigned *w); /* returns 1 for a matrix, 0 for a scalar */
 void cg_value_get(const cg_function *f, float *dst);
 bool cg_all_less_than(const cg_function *f, float x);

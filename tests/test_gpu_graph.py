@@ -268,6 +268,63 @@ def test_corrected_activation_gradients_match_the_oracle(cg, oracle, mode):
         cg.set_mode("exact")
 
 
+def test_eval_and_symbolic_grad(cg):
+    """SURVEY §8 row f4 — `eval` and the symbolic `grad` of src/optimize.rs:8-56 on the same kernels (the README's
+    "backprop vs naive" comparison). eval against closed forms; grad against the analytic derivative, element by
+    element, and against finite differences of eval; and the README's claim itself: one backprop step (with the chain
+    rule completed, cg_set_fix_act_grad) moves the parameter by -lr * mean(grad.eval()) in total — "in total" because
+    every use site of x is its own copy (Q1) and receives its own share, and "mean" because that is the reference's
+    scalar <- matrix rule (Q5). Neither call may change a parameter."""
+    F = cg.Function
+    rng = np.random.default_rng(12)
+    mv = rng.uniform(-1, 1, (5, 7)).astype(np.float32)
+    x0 = np.float32(0.37)
+
+    def build():
+        x = F.scalar_param("x", float(x0))
+        m = F.constant(cg.Constant(mv))
+        return ((x * m + x.sq()).tanh() - (x * m).sigmoid()) * x.abs(), x
+
+    def closed(xv):
+        xv = np.float64(xv)
+        u = xv * mv.astype(np.float64) + xv * xv
+        s = 1.0 / (1.0 + np.exp(-xv * mv.astype(np.float64)))
+        val = (np.tanh(u) - s) * abs(xv)
+        du = (1 - np.tanh(u) ** 2) * (mv + 2 * xv) - s * (1 - s) * mv
+        return val, du * abs(xv) + (np.tanh(u) - s) * np.sign(xv)
+
+    f, x = build()
+    val, dval = closed(x0)
+    got = np.asarray(f.eval({}))
+    assert got.shape == (5, 7) and rel_err(got, val) < 1e-5
+    g = f.grad("x")
+    gv = np.asarray(g.eval({}))
+    assert rel_err(gv, dval) < 1e-4
+    # finite differences of eval (float32 forward: a loose bound)
+    eps = 1e-2
+    fp, _ = build()
+    hi = np.asarray((F.scalar(float(x0 + eps)) * F.constant(cg.Constant(mv))).eval({}))  # eval of a constant-only graph
+    assert rel_err(hi, (x0 + eps) * mv) < 1e-6
+    assert rel_err(gv, (closed(x0 + eps)[0] - closed(x0 - eps)[0]) / (2 * eps)) < 1e-2
+    # nothing moved
+    assert all(float(v) == float(x0) for n, v in f.leaves() if n == "x")
+    # backprop vs naive: the same update
+    cg.set_fix_act_grad(True)
+    try:
+        f2, _ = build()
+        f2.minimize({}, 0.01, 1)
+        moved = sum((float(x0) - float(v)) / 0.01 for n, v in f2.leaves() if n == "x")
+    finally:
+        cg.set_fix_act_grad(False)
+    assert abs(moved - float(gv.astype(np.float64).mean())) < 2e-3 * max(1.0, abs(float(gv.mean())))
+    # an input named like the parameter, products, signum: the reference's panics
+    w = F.param("w", cg.Constant(mv))
+    for bad, msg in ((cg.dot(F.constant(cg.Constant(mv.T.copy())), w), "not implemented"), (w.signum(), "nondifferentiable")):
+        with pytest.raises(Exception, match=msg):
+            bad.grad("w")
+    assert float(np.asarray(w.sq().grad("nope").eval({}))) == 0.0  # a parameter the function does not mention
+
+
 def test_medium_lstm_tiled_gemm(cg, oracle):
     """Products above the strict-kernel limit take the tiled FP32 SIMT kernel (FMA accumulation): 1e-5."""
     cg.set_mode("dag")

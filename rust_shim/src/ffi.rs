@@ -37,6 +37,10 @@ extern "C" {
     pub fn cg_maximize(f: *mut CgFunction, nargs: c_int, names: *const *const c_char, vals: *const *const c_float,
                        hs: *const c_uint, ws: *const c_uint, learn_rate: c_float, iters: c_int, print_freq: c_int,
                        trace: *mut c_float) -> c_int;
+    // optimize.rs:8-56
+    pub fn cg_eval(f: *mut CgFunction, nargs: c_int, names: *const *const c_char, vals: *const *const c_float,
+                   hs: *const c_uint, ws: *const c_uint, dst_colmajor: *mut c_float) -> c_int;
+    pub fn cg_grad(f: *const CgFunction, param: *const c_char) -> *mut CgFunction;
     // read-back (ops.rs:309-329, print.rs)
     pub fn cg_value_dims(f: *const CgFunction, h: *mut c_uint, w: *mut c_uint) -> c_int;
     pub fn cg_value_get(f: *const CgFunction, dst_colmajor: *mut c_float);

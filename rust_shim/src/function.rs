@@ -111,6 +111,12 @@ impl Function {
     /// observable through the handle, and lstm.rs only ever passes `random_param`s, so this is a no-op.
     pub fn check_params(_functions: Vec<&Function>) {}
 
+    /// Shape of the value ([] for a scalar), known from construction on.
+    pub fn dims(&self) -> Vec<usize> {
+        let (mut h, mut w) = (0 as c_uint, 0 as c_uint);
+        if unsafe { cg_value_dims(self.h, &mut h, &mut w) } != 0 { vec![h as usize, w as usize] } else { vec![] }
+    }
+
     // ---- read-back ----------------------------------------------------------------------------------------
     /// The cached forward value (row-major for a matrix). After `minimize(n)` it is the forward value of the
     /// last iteration, i.e. at the parameters after n-1 updates (optimize.rs:64-71).

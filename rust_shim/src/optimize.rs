@@ -3,7 +3,7 @@
 //! fused tape and replays it (CUDA graph, or one resident CTA for latency-bound graphs) `iters` times.
 use constant::Constant;
 use ffi::*;
-use function::{last_error, Function};
+use function::{check, last_error, Function};
 use libc::{c_char, c_float, c_int, c_uint};
 use std::collections::HashMap;
 use std::ffi::CString;
@@ -44,6 +44,38 @@ fn flatten(args: &HashMap<&str, Constant>) -> FlatArgs {
 }
 
 impl Function {
+    /// optimize.rs:8-32 — the forward value at the current parameters; nothing cached changes.
+    pub fn eval(&self, args: &HashMap<&str, Constant>) -> Constant {
+        let a = flatten(args);
+        let dims = self.dims();
+        let n = if dims.is_empty() { 1 } else { dims[0] * dims[1] };
+        let mut colmajor = vec![0f32; n];
+        let rc = unsafe {
+            cg_eval(self.h, a.name_ptrs.len() as c_int, a.name_ptrs.as_ptr(), a.val_ptrs.as_ptr(), a.hs.as_ptr(),
+                    a.ws.as_ptr(), colmajor.as_mut_ptr())
+        };
+        if rc != 0 {
+            panic!("{}", last_error());
+        }
+        if dims.is_empty() {
+            return Constant::Scalar(colmajor[0]);
+        }
+        let (h, w) = (dims[0], dims[1]);
+        let mut rowmajor = vec![0f32; n];
+        for j in 0..w {
+            for i in 0..h {
+                rowmajor[i * w + j] = colmajor[j * h + i];
+            }
+        }
+        Constant::matrix(h, w, rowmajor)
+    }
+
+    /// optimize.rs:34-56 — d self / d param as a new Function (the README's "naive" gradient).
+    pub fn grad(&self, param: &str) -> Function {
+        let name = CString::new(param).unwrap();
+        Function { h: check(unsafe { cg_grad(self.h, name.as_ptr()) }) }
+    }
+
     pub fn minimize(&self, args: &HashMap<&str, Constant>, learn_rate: f32, iters: i32, print_freq: i32) {
         let a = flatten(args);
         let rc = unsafe {

@@ -147,7 +147,7 @@ constexpr int DP_MAX_WORLD = 8;
 constexpr int DP_THREADS = 512;
 constexpr int DP_DEFAULT_CTAS = 64;  // CG_DP_CTAS overrides
 int dp_max_ctas();
-constexpr unsigned long long DP_WAIT_TIMEOUT_NS = 4000000000ull;  // 4 s: a lost rank raises an error, never hangs the GPU
+constexpr unsigned long long DP_WAIT_TIMEOUT_NS = 4000000000ull;  // default 4 s (CG_DP_TIMEOUT_MS): a lost rank raises an error, never hangs the GPU
 enum { DP_FLAG_A = 0, DP_FLAG_B = 16, DP_FLAG_EPOCH = 32, DP_FLAG_TICKET = 33, DP_FLAG_ERR = 34, DP_FLAG_WORDS = 64 };
 struct DpReduceArgs {
   const float* g[DP_MAX_WORLD];  // the partial gradient in every rank (index = rank)
@@ -156,6 +156,7 @@ struct DpReduceArgs {
   float lr;
   size_t n;
   int rank, world;
+  unsigned long long timeout_ns;  // bound of every flag wait
 };
 void launch_dp_reduce_update(const DpReduceArgs& a, cudaStream_t stream);
 // Collective (every rank, same order): makes the cudaMalloc allocations that contain these pointers addressable from

@@ -330,6 +330,12 @@ void dp_fill_flags(DpReduceArgs& a) {
   for (int r = 0; r < DP_MAX_WORLD; r++) a.flags[r] = static_cast<uint32_t*>(peers[r]);
   a.rank = g_nccl.rank;
   a.world = g_nccl.world;
+  static const unsigned long long timeout_ns = [] {
+    const char* e = getenv("CG_DP_TIMEOUT_MS");  // how long an exchange waits for a peer before it reports a lost rank
+    const long long ms = e ? atoll(e) : 0;
+    return ms > 0 ? (unsigned long long)ms * 1000000ull : DP_WAIT_TIMEOUT_NS;
+  }();
+  a.timeout_ns = timeout_ns;
 }
 
 void dp_check_errors() {

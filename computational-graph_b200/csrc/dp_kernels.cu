@@ -49,12 +49,13 @@ __device__ __forceinline__ void st_stream(float* p, const float4& v) {
 // waits until flags[base + q] >= epoch for every rank q (thread q of the CTA polls rank q's flag). Once an exchange has
 // timed out (err != 0) nothing waits any more: the remaining kernels of the iteration drain at once and the host
 // raises the error after its next synchronisation (dp_check_errors).
-__device__ __forceinline__ void wait_all(const uint32_t* own, int base, int world, uint32_t epoch, uint32_t* err) {
+__device__ __forceinline__ void wait_all(const uint32_t* own, int base, int world, uint32_t epoch, uint32_t* err,
+                                         unsigned long long timeout_ns) {
   if ((int)threadIdx.x < world) {
     const unsigned long long t0 = global_ns();
     while ((int)(ld_acquire_sys(own + base + threadIdx.x) - epoch) < 0) {
       if (ld_acquire_sys(err) != 0) break;
-      if (global_ns() - t0 > DP_WAIT_TIMEOUT_NS) {
+      if (global_ns() - t0 > timeout_ns) {
         st_release_sys(err, 1u);
         break;
       }
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(DP_THREADS, 2) dp_reduce_update_kernel(const D
 
   // ---- barrier A: every rank's partial gradient is complete, and every rank is done reading the old weight ----
   if (blockIdx.x == 0 && (int)threadIdx.x < WORLD) st_release_sys(a.flags[threadIdx.x] + DP_FLAG_A + a.rank, epoch);
-  wait_all(own, DP_FLAG_A, WORLD, epoch, own + DP_FLAG_ERR);
+  wait_all(own, DP_FLAG_A, WORLD, epoch, own + DP_FLAG_ERR, a.timeout_ns);
 
   // ---- this rank's slice: sum over ranks in rank order, update once, store everywhere -------------------------
   const size_t n4 = a.n / 4;  // the caller guarantees n % 4 == 0 and 16-byte aligned buffers
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(DP_THREADS, 2) dp_reduce_update_kernel(const D
   if (!s_last) return;
   __threadfence_system();
   if ((int)threadIdx.x < WORLD) st_release_sys(a.flags[threadIdx.x] + DP_FLAG_B + a.rank, epoch);
-  wait_all(own, DP_FLAG_B, WORLD, epoch, own + DP_FLAG_ERR);
+  wait_all(own, DP_FLAG_B, WORLD, epoch, own + DP_FLAG_ERR, a.timeout_ns);
   if (threadIdx.x == 0) {
     own[DP_FLAG_TICKET] = 0;
     own[DP_FLAG_EPOCH] = epoch;

@@ -100,3 +100,15 @@ def test_data_parallel_tape(plans):
             assert ex[0] < 20 and ex[34] < 160  # half of the exchanges are issued in the first half of the iteration
         else:
             assert ex[0] > 69
+
+
+def test_random_graphs_plan_and_compile():
+    """tests/plan_fuzz.py: random expression trees (every operator, scalar / matrix mixes, broadcasts, scalar <- matrix
+    means, square products) plan in both modes with and without hoisting — the hoisting pass re-verifies every
+    dependency itself — and the small ones come out as compiled resident kernels that NVRTC accepts for sm_100a."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "plan_fuzz.py"), "7", "30"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["errors"] == [] and out["graphs"] == 30 and out["plans"] == 120
+    assert out["compiled"] >= 90 and out["with_means"] > 0

@@ -263,3 +263,30 @@ def test_corrected_activation_gradients_match_finite_differences(oracle):
         scale = np.max(np.abs(want[k]))
         assert np.max(np.abs(got[1][k] - want[k])) < 2e-2 * scale, k      # corrected rule: the true gradient
         assert np.max(np.abs(got[0][k] - want[k])) > 0.3 * scale, k       # reference rule (Q3): not a gradient
+
+
+def test_random_graphs_port_vs_reference_backend_and_exact_vs_dag(oracle):
+    """Random expression trees (tests/plan_fuzz.py's generator: every operator, scalar / matrix mixes, broadcasts,
+    scalar <- matrix means, square products) through the oracle: the port's arithmetic must equal the reference-compiled
+    backend's bit for bit, and — a tree has no shared non-leaf — dag mode must equal exact mode bit for bit."""
+    from plan_fuzz import random_graph
+    if not oracle.use_ref("O0"):
+        pytest.skip("oracle/_ref is not built")
+    try:
+        for g in range(25):
+            runs = []
+            for backend, mode in (("ref", "exact"), ("port", "exact"), ("port", "dag")):
+                oracle.use_ref("O0") if backend == "ref" else oracle.use_port()
+                oracle.set_mode(mode)
+                f = random_graph(oracle, np.random.default_rng(1000 + g), 1 + g % 5)
+                tr = np.asarray(f.minimize({}, 0.01, 3, trace=True))
+                runs.append((tr, [np.asarray(v) for _, v in f.leaves()]))
+            for other in runs[1:]:
+                assert np.array_equal(runs[0][0].view(np.int32), other[0].view(np.int32)), g
+                assert len(runs[0][1]) == len(other[1])
+                for a, b in zip(runs[0][1], other[1]):
+                    assert np.array_equal(a.view(np.int32), b.view(np.int32)), g
+    finally:
+        oracle.set_mode("exact")
+        if not oracle.use_ref("O0"):
+            oracle.use_port()

@@ -412,7 +412,6 @@ void launch_io_graph(Plan& p, Runtime& rt, const std::vector<Arg>& args, float* 
     CG_CUDA(cudaEventRecord(p.io_done, rt.stream));
     CG_CUDA(cudaStreamWaitEvent(copy, p.io_done, 0));
     static const bool dbg = getenv("CG_DEBUG_TIMING") != nullptr;
-    static const bool skip = getenv("CG_IO_SKIP_COPY") != nullptr;  // bring-up probe: pretend the inputs have landed
     static cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (dbg && !t0) {
       cudaEventCreate(&t0);
@@ -420,7 +419,7 @@ void launch_io_graph(Plan& p, Runtime& rt, const std::vector<Arg>& args, float* 
     }
     if (dbg) cudaEventRecord(t0, copy);
     for (size_t i : g.order) {
-      if (!skip) CG_CUDA(cudaMemcpyAsync(g.h2d_dst[i], src[i], g.h2d_bytes[i], cudaMemcpyHostToDevice, copy));
+      CG_CUDA(cudaMemcpyAsync(g.h2d_dst[i], src[i], g.h2d_bytes[i], cudaMemcpyHostToDevice, copy));
       CG_CUDA(cudaEventRecord(g.in_ev[i], copy));
     }
     if (dbg) {

@@ -174,6 +174,11 @@ int cg_leaf_set(cg_function* f, int i, const float* src) {
     leaves[i]->value.summary_valid = false;
   });
 }
+unsigned long long cg_leaf_address(cg_function* f, int i) {
+  auto leaves = collect_param_leaves(*F(f));
+  if (i < 0 || i >= (int)leaves.size() || !leaves[i]->value.buf) return 0;
+  return (unsigned long long)(uintptr_t)leaves[i]->value.buf->ptr;
+}
 int cg_kind(const cg_function* f) { return (int)F(f)->body->kind; }
 
 // ---- switches --------------------------------------------------------------------------------------------------------

@@ -648,6 +648,27 @@ const TapeKernel* tape_jit_build(const Plan& p, bool load) {
       fputs(src.c_str(), f);
       fclose(f);
     }
+    // Plan-only mode: next to the source, what a launch needs — the pointer table with the initial contents of every
+    // persistent buffer — so that tests/tape_emu can execute the generated source on the CPU (test infrastructure;
+    // the product never does). Little-endian: u64 count, root_off, root_n, root_is_leaf, smem_floats; then per
+    // table entry u64 address, n, offset, written and n floats.
+    if (plan_only()) {
+      if (FILE* f = fopen((std::string(path) + ".table").c_str(), "wb")) {
+        auto put = [&](unsigned long long v) { fwrite(&v, sizeof v, 1, f); };
+        std::unordered_map<const float*, const TapeBuf*> at;
+        for (const TapeBuf& b : bufs) at[b.ptr] = &b;
+        put(k->ptrs.size()), put(at.at(p.root_ptr)->off), put(p.root_n), put(p.root_is_leaf ? 1 : 0), put(total);
+        for (float* ptr : k->ptrs) {
+          const TapeBuf& b = *at.at(ptr);
+          put((unsigned long long)(uintptr_t)ptr), put(b.n), put(b.off), put(b.written ? 1 : 0);
+          std::vector<float> init(b.n, 0.0f);
+          if (const std::vector<float>* sh = plan_only_shadow(ptr))
+            for (size_t i = 0; i < b.n && i < sh->size(); i++) init[i] = (*sh)[i];
+          fwrite(init.data(), sizeof(float), b.n, f);
+        }
+        fclose(f);
+      }
+    }
   }
   k->smem_bytes = total * sizeof(float);
   std::lock_guard<std::mutex> lock(g_mu);

@@ -1,8 +1,10 @@
 // graph.cpp — graph construction with the reference's semantics (function.rs, ops.rs constructors).
 #include "graph.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <unordered_map>
 #include <unordered_set>
 
 namespace cg {
@@ -17,7 +19,16 @@ static void no_device(const char* what) {
   throw Error(std::string("plan-only mode: ") + what + " needs a CUDA device (this backend has no CPU path)");
 }
 
+static std::unordered_map<const float*, std::weak_ptr<std::vector<float>>> g_shadows;  // plan-only: placeholder -> contents
+const std::vector<float>* plan_only_shadow(const float* ptr) {
+  auto it = g_shadows.find(ptr);
+  if (it == g_shadows.end()) return nullptr;
+  auto sp = it->second.lock();
+  return sp ? sp.get() : nullptr;  // (the owning DevBuf keeps it alive for as long as the plan can name the buffer)
+}
+
 DevBuf::~DevBuf() {
+  if (placeholder) g_shadows.erase(ptr);
   if (owned && ptr && !placeholder) {
     dp_forget(ptr, (n ? n : 1) * sizeof(float));  // peers may hold this buffer open (dp.cpp)
     cudaFree(ptr);
@@ -33,6 +44,10 @@ BufRef DevBuf::alloc(size_t n) {
     b->ptr = reinterpret_cast<float*>(next);
     next += (((n ? n : 1) * sizeof(float)) + 255) / 256 * 256;
     b->placeholder = true;
+    if (n <= 65536) {  // resident plans only
+      b->shadow = std::make_shared<std::vector<float>>(n ? n : 1, 0.0f);
+      g_shadows[b->ptr] = b->shadow;
+    }
     return b;
   }
   CG_CUDA(cudaMalloc(&b->ptr, (n ? n : 1) * sizeof(float)));
@@ -75,7 +90,7 @@ void Runtime::init() {
 }
 
 static void fill_device(float* ptr, size_t n, float v) {
-  if (g_plan_only) return;
+  if (g_plan_only) return;  // (the caller fills the shadow)
   Runtime& rt = Runtime::get();
   EwProgram p{};
   p.n = n;
@@ -110,12 +125,23 @@ Function* make_scalar_leaf(Kind kind, const char* name, float x) {
   if (!g_plan_only) {
     CG_CUDA(cudaMemcpyAsync(v.buf->ptr, &x, sizeof(float), cudaMemcpyHostToDevice, rt.stream));
     CG_CUDA(cudaStreamSynchronize(rt.stream));
+  } else if (v.buf->shadow) {
+    (*v.buf->shadow)[0] = x;
   }
   return new_leaf(kind, name, std::move(v));
 }
 
 void value_upload_rowmajor(Value& v, const float* src, bool sync) {
-  if (g_plan_only) return;
+  if (g_plan_only) {
+    // the layout change the upload kernel would do: row-major host values -> column-major storage
+    if (!v.buf->shadow) return;
+    std::vector<float>& sh = *v.buf->shadow;
+    if (!v.is_matrix) sh[0] = src[0];
+    else
+      for (unsigned i = 0; i < v.h; i++)
+        for (unsigned j = 0; j < v.w; j++) sh[(size_t)j * v.h + i] = src[(size_t)i * v.w + j];
+    return;
+  }
   // Matrix::new -> set_array(values, transpose = true) (matrix.rs:59-66, cpu/matrix.cpp:26-36)
   Runtime& rt = Runtime::get();
   const size_t n = v.size();
@@ -162,7 +188,10 @@ Function* make_fill_leaf(Kind kind, const char* name, unsigned h, unsigned w, fl
   v.uval = x;
   v.buf = DevBuf::alloc((size_t)h * w);
   fill_device(v.buf->ptr, (size_t)h * w, x);
-  if (g_plan_only) return new_leaf(kind, name, std::move(v));
+  if (g_plan_only) {
+    if (v.buf->shadow) std::fill(v.buf->shadow->begin(), v.buf->shadow->end(), x);
+    return new_leaf(kind, name, std::move(v));
+  }
   rt.launches++;
   CG_CUDA(cudaStreamSynchronize(rt.stream));
   return new_leaf(kind, name, std::move(v));
@@ -189,6 +218,8 @@ static Value clone_value(const Value& v) {
     if (!g_plan_only) {
       CG_CUDA(cudaMemcpyAsync(c.buf->ptr, v.buf->ptr, v.size() * sizeof(float), cudaMemcpyDeviceToDevice, rt.stream));
       CG_CUDA(cudaStreamSynchronize(rt.stream));
+    } else if (v.buf->shadow && c.buf->shadow) {
+      *c.buf->shadow = *v.buf->shadow;
     }
   }
   return c;

@@ -22,6 +22,9 @@ struct DevBuf {
   std::shared_ptr<void> keepalive;  // arena that owns `ptr`, when not owned here
   bool owned = false;
   bool placeholder = false;  // plan-only mode: an address that is never dereferenced
+  // plan-only mode: the INITIAL contents (storage order) this buffer would have been given — never computed on, only
+  // written out next to the generated resident-kernel source (CG_TAPE_JIT_DUMP) for the CPU-side emulator test
+  std::shared_ptr<std::vector<float>> shadow;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -68,6 +71,7 @@ struct Expr {
 
 inline bool is_leaf(Kind k) { return k == Kind::Constant || k == Kind::Input || k == Kind::Param; }
 
+const std::vector<float>* plan_only_shadow(const float* placeholder);  // plan-only: initial contents of a buffer, or null
 bool plan_only();
 void set_plan_only(bool on);
 

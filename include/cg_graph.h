@@ -77,6 +77,9 @@ int cg_eval(cg_function *f, int nargs, const char **names, const float **arg_val
 /* `f.grad(param)` (src/optimize.rs:34-56): a NEW function, d f / d param, built symbolically (the README's "naive"
  * gradient; products are "not implemented", as in the reference). d(f^2) = 2 f f' — the reference drops the 2. */
 cg_function *cg_grad(const cg_function *f, const char *param);
+/* The device address of leaf i's storage (in plan-only mode: its placeholder) — identifies the leaf in a dumped
+ * resident-kernel pointer table (CG_TAPE_JIT_DUMP). 0 when out of range. */
+unsigned long long cg_leaf_address(cg_function *f, int i);
 int cg_value_dims(const cg_function *f, unsigned *h, unsigned *w); /* returns 1 for a matrix, 0 for a scalar */
 void cg_value_get(const cg_function *f, float *dst);
 bool cg_all_less_than(const cg_function *f, float x);

@@ -59,7 +59,13 @@ def cases(api):
         b = F.matrix(3, 4, list(np.linspace(-1, 1.5, 12)))
         return (((x - F.scalar(2.)) * (m + b) - F.scalar(10.)).sq() + (x * m).tanh()).abs()
 
+    from plan_fuzz import random_graph
+    fuzz = {}
+    for g in (8, 29, 49, 50, 53, 59):  # seeds whose graphs fold no constants at construction and take >= 3 kernels
+        fuzz[f"random_{g}"] = (lambda a, g=g: random_graph(a, np.random.default_rng(5000 + g), 1 + g % 5),
+                               "exact" if g % 2 else "dag", 0.01, 3)
     return {
+        **fuzz,
         "c3_exact_d5": (lambda a: readme_lstm(a, 5), "exact", 0.01, 6),
         "c3_dag_d6": (lambda a: readme_lstm(a, 6), "dag", 0.01, 6),
         "c3_exact_d17": (lambda a: readme_lstm(a, 17), "exact", 0.01, 3),   # odd size: blocked product edges, vec-4 tails

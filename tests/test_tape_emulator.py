@@ -21,7 +21,8 @@ def emulated():
 
 
 @pytest.mark.parametrize("case", ["c1", "broadcast_avg", "c3_exact_d5", "c3_dag_d6", "c3_exact_d17", "c3_dag_d30",
-                                  "lstm_T3_nonsquare"])
+                                  "lstm_T3_nonsquare", "random_8", "random_29", "random_49", "random_50", "random_53",
+                                  "random_59"])
 def test_generated_resident_kernel_equals_the_oracle_bit_for_bit(emulated, case):
     r = emulated[case]
     assert r["bit_identical"], r

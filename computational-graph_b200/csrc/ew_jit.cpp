@@ -594,10 +594,13 @@ std::string tape_source(const Plan& p, const std::vector<TapeBuf>& bufs, std::ve
     if (st.kind == Step::EW) {
       const EwProgram& pr = st.prog;
       s << "    {  // step " << i << ": elementwise, n = " << pr.n << "\n      const u64 n = " << pr.n << ";\n";
-      for (uint32_t k = 0; k < pr.n_in; k++)
-        if ((pr.in_scalar_mask >> k) & 1u) s << "      const float s" << k << " = S[" << off(pr.in[k]) << "];\n";
       const int vec = pr.n <= TAPE_SMALL ? 1 : 4;
       s << "      for (u64 b = (u64)((t + T - " << shift << ") & (T - 1)) * " << vec << "; b < n; b += T * " << vec << ") {\n";
+      // scalar operands are read INSIDE the loop, i.e. only by the threads that take part in the step: a program that
+      // updates a scalar in place (x <- x - e) would otherwise have every idle thread read x while one thread writes
+      // it — a value nobody uses, but a data race all the same (found by the ThreadSanitizer run of tests/tape_emu)
+      for (uint32_t k = 0; k < pr.n_in; k++)
+        if ((pr.in_scalar_mask >> k) & 1u) s << "        const float s" << k << " = S[" << off(pr.in[k]) << "];\n";
       EwOperands o;
       o.in = [&](uint32_t k) { return "S + " + off(pr.in[k]); };
       o.out = [&](uint32_t k) { return "S + " + off(pr.out[k]); };

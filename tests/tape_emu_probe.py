@@ -31,12 +31,18 @@ def read_table(path):
     return root_n, entries
 
 
-def emulate(src, iters, workdir):
-    exe = os.path.join(workdir, "emu")
+def emulate(src, iters, workdir, sanitize=False):
+    """Compiles the generated source behind the shim and runs it. sanitize=True builds with ThreadSanitizer and returns
+    the number of data-race reports instead: the CTA's threads are real threads here, so a barrier the generator failed
+    to place between two dependent steps is a reported race (checked: removing one __syncthreads() is caught)."""
+    exe = os.path.join(workdir, "emu_tsan" if sanitize else "emu")
     subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-Wno-unknown-pragmas", "-I", EMU,
                     "-include", os.path.join(EMU, "shim.h"), f'-DTAPE_SOURCE="{src}"', os.path.join(EMU, "glue.cpp"),
-                    os.path.join(EMU, "driver.cpp"), "-o", exe], check=True)
+                    os.path.join(EMU, "driver.cpp"), "-o", exe] + (["-g", "-fsanitize=thread"] if sanitize else []), check=True)
     out = os.path.join(workdir, "out.bin")
+    if sanitize:
+        r = subprocess.run([exe, src + ".table", str(iters), out], capture_output=True, text=True, timeout=900)
+        return r.stderr.count("WARNING: ThreadSanitizer")
     subprocess.run([exe, src + ".table", str(iters), out], check=True, timeout=600)
     root_n, entries = read_table(src + ".table")
     data = np.fromfile(out, dtype=np.float32)
@@ -115,6 +121,8 @@ def main():
                 worst = max(worst, float(np.max(np.abs(got.astype(np.float64) - want)) / max(np.max(np.abs(want)), 1e-30)))
             out[name] = {"bit_identical": exact, "worst_rel_err": worst, "kernels": st["kernels_per_iter"],
                          "smem_bytes": st["tape_smem_bytes"], "leaves": n_leaves, "iters": iters}
+            if name in ("c3_exact_d5", "c3_dag_d6", "lstm_T3_nonsquare", "broadcast_avg", "random_59"):
+                out[name]["races"] = emulate(src, 2, tmp, sanitize=True)
     orc.set_mode("exact")
     print(json.dumps(out))
 

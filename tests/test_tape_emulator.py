@@ -27,3 +27,10 @@ def test_generated_resident_kernel_equals_the_oracle_bit_for_bit(emulated, case)
     r = emulated[case]
     assert r["bit_identical"], r
     assert r["worst_rel_err"] == 0.0 and r["smem_bytes"] > 0 and r["leaves"] >= 1
+
+
+@pytest.mark.parametrize("case", ["c3_exact_d5", "c3_dag_d6", "lstm_T3_nonsquare", "broadcast_avg", "random_59"])
+def test_generated_resident_kernel_has_no_data_race(emulated, case):
+    """The generator schedules steps by dependency level and puts a __syncthreads() only between levels; under
+    ThreadSanitizer (the CTA's 512 threads are OS threads in the emulator) a missing barrier is a reported data race."""
+    assert emulated[case]["races"] == 0, emulated[case]

@@ -12,61 +12,53 @@ pub enum Constant {
 }
 
 impl Constant {
-    /// 1 for a scalar, else the matrix width (constant.rs:12-17).
-    pub fn width(&self) -> usize {
-        match *self {
-            Constant::Scalar(_) => 1,
-            Constant::Matrix(ref m) => m.width(),
-        }
+    fn shape(&self) -> (usize, usize) {
+        if let Constant::Matrix(ref m) = *self { (m.height(), m.width()) } else { (1, 1) }
     }
 
-    /// 1 for a scalar, else the matrix height (constant.rs:20-25).
-    pub fn height(&self) -> usize {
-        match *self {
-            Constant::Scalar(_) => 1,
-            Constant::Matrix(ref m) => m.height(),
-        }
-    }
+    /// Matrix height, 1 for a scalar (same contract as the reference's accessor, constant.rs:20-25).
+    pub fn height(&self) -> usize { self.shape().0 }
 
+    /// Matrix width, 1 for a scalar (constant.rs:12-17).
+    pub fn width(&self) -> usize { self.shape().1 }
+
+    /// `[]` for a scalar, `[height, width]` for a matrix.
     pub fn dims(&self) -> Vec<usize> {
-        match *self {
-            Constant::Scalar(_) => vec![],
-            Constant::Matrix(ref m) => vec![m.height(), m.width()],
-        }
+        if let Constant::Matrix(ref m) = *self { vec![m.height(), m.width()] } else { Vec::new() }
     }
 
-    /// constant.rs:36-42
+    /// A value whose every element is `val`; `dims` is `[]` or `[height, width]` (constant.rs:36-42).
     pub fn single_val(dims: Vec<usize>, val: f32) -> Constant {
-        match dims.len() {
-            0 => Constant::Scalar(val),
-            2 => Constant::Matrix(Matrix::single_val(dims[0], dims[1], val)),
-            _ => panic!("not supported"),
+        if dims.is_empty() {
+            return Constant::Scalar(val);
         }
+        assert!(dims.len() == 2, "not supported");
+        Constant::Matrix(Matrix::single_val(dims[0], dims[1], val))
     }
 
-    /// constant.rs:45-60 — unseeded uniform draws, as in the reference.
+    /// Uniform draws from [lo, hi) with the thread-local generator — unseeded, like the reference (constant.rs:45-60).
     pub fn random(dims: Vec<usize>, lo: f32, hi: f32) -> Constant {
-        let between = Range::new(lo, hi);
+        let dist = Range::new(lo, hi);
         let mut rng = rand::thread_rng();
-        match dims.len() {
-            0 => Constant::Scalar(between.ind_sample(&mut rng)),
-            2 => {
-                let vals = (0..dims[0] * dims[1]).map(|_| between.ind_sample(&mut rng)).collect();
-                Constant::matrix(dims[0], dims[1], vals)
-            }
+        let count = match dims.len() {
+            0 => 1,
+            2 => dims[0] * dims[1],
             _ => panic!("not supported"),
+        };
+        let mut draws: Vec<f32> = Vec::with_capacity(count);
+        while draws.len() < count {
+            draws.push(dist.ind_sample(&mut rng));
         }
+        if dims.is_empty() { Constant::Scalar(draws[0]) } else { Constant::matrix(dims[0], dims[1], draws) }
     }
 
-    /// Row-major values (constant.rs:62-76).
+    /// Values in ROW-major order, the order the reference's constructor takes them in (constant.rs:62-76).
     pub fn matrix(height: usize, width: usize, vals: Vec<f32>) -> Constant {
         Constant::Matrix(Matrix::new(height, width, vals))
     }
 
+    /// The scalar itself, or the mean of a matrix (ops.rs:430-442).
     pub fn avg(&self) -> f32 {
-        match *self {
-            Constant::Scalar(x) => x,
-            Constant::Matrix(ref m) => m.avg(),
-        }
+        if let Constant::Matrix(ref m) = *self { m.avg() } else if let Constant::Scalar(x) = *self { x } else { unreachable!() }
     }
 }

@@ -3,6 +3,12 @@
 // reference has no batch normalisation of the loss — root error == 1, optimize.rs:69 — so gradients
 // add, they are not averaged). The reference itself has no distributed code at all.
 //
+// The sum itself is done by the fused exchange kernel of dp_kernels.cu whenever the ranks can address each other's
+// memory: this file opens every gradient slot and weight of a plan in every peer through CUDA IPC ("windows":
+// per-buffer (allocation handle, offset) pairs exchanged over an NCCL all-gather, every rank agreeing on the outcome)
+// and hands the kernel the peer pointers and the flag blocks. ncclAllReduce remains for weights too small to be
+// worth a window, for machines without peer access and for CG_DP_FUSED=0.
+//
 // NCCL is resolved with dlopen at cg_dp_init time, so the library loads (and every single-GPU path
 // runs) on machines without NCCL, and a process that already carries torch's NCCL reuses that copy.
 #include <cuda.h>

@@ -1,7 +1,8 @@
 """Data-parallel host logic for the batch-sharded LSTM. The reference has no distributed code; this
 is the one new exchange step the path gets: every rank owns a contiguous block of batch rows of the inputs, the
 target and the row-shaped parameters (biases, h0, C0 — full [batch, H] matrices in the reference, src/lstm.rs:63-75),
-weights are replicated, and each weight gradient X^T.E is SUM-all-reduced before its update (root error == 1,
+weights are replicated, and each weight gradient X^T.E is SUMMED over the ranks before its update — by the library's
+fused all-reduce + update kernel over NVLink peer memory, or by ncclAllReduce (csrc/dp.cpp) — (root error == 1,
 src/optimize.rs:69: gradients add, they are not averaged)."""
 from __future__ import annotations
 

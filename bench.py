@@ -260,6 +260,8 @@ def main():
     ap.add_argument("--config", default=os.environ.get("CG_BENCH_CONFIG", "c4"), choices=["c4", "c5"],
                     help="c4 (default): BASELINE config 4, weak scaling; c5: BASELINE config 5, T=32, global batch 8192, strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multimem", default="auto", choices=["auto", "on", "off"],
+                    help="N > 1: in-switch (NVLS multimem) weight exchange — auto: from three ranks up")
     ap.add_argument("--cpu-configs", action="store_true",
                     help="with --impl reference: time the reference CPU path on the secondary configs C1-C3 instead")
     args = ap.parse_args()
@@ -284,6 +286,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         pkg.dp.init_from_torch_distributed(api, local_rank)
+        if args.multimem != "auto":
+            api.dp_set_multimem(2 if args.multimem == "on" and api.dp_multimem_supported() else 0)
     api.set_mode("dag")
     api.set_tf32(args.product == "tf32")
 
@@ -381,8 +385,8 @@ def main():
         "plan": stats,
     }
     if world > 1:
-        line["exchange"] = ("fused all-reduce + SGD update kernel over NVLink peer memory (CUDA IPC)" if api.dp_fused()
-                            else "ncclAllReduce + elementwise update")
+        line["exchange"] = api.dp_exchange_name()
+        line["multimem_supported"] = api.dp_multimem_supported() or api.dp_multimem_reason()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         its, scaled, kind, desc = cpu_sample(2, 0)
         line["cpu_baseline"] = {"value": scaled, "unit": "iterations/s", "cores": 1, "kind": kind, "sample": desc}

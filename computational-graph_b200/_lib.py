@@ -39,7 +39,8 @@ class PlanStats(C.Structure):
                                              "gemms_fused_sgd", "reduces", "arena_bytes")] + \
                [("gemm_flop_per_iter", C.c_double), ("ew_bytes_per_iter", C.c_double), ("ew_specialised", C.c_ulonglong),
                 ("allreduces", C.c_ulonglong), ("dp_fused_updates", C.c_ulonglong), ("vm_resident", C.c_ulonglong), ("tape_smem_bytes", C.c_ulonglong),
-                ("quiet_variant", C.c_ulonglong), ("quiet_ew_bytes_per_iter", C.c_double)]
+                ("quiet_variant", C.c_ulonglong), ("quiet_ew_bytes_per_iter", C.c_double),
+                ("dp_multimem_updates", C.c_ulonglong)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -66,6 +67,10 @@ class ProductApi(Api):
         lib.cg_dp_init.restype, lib.cg_dp_init.argtypes = C.c_int, [C.c_int, C.c_int, C.c_char_p]
         lib.cg_dp_shutdown.restype = C.c_int
         lib.cg_dp_fused.restype = C.c_int
+        lib.cg_dp_multimem.restype = C.c_int
+        lib.cg_dp_multimem_supported.restype = C.c_int
+        lib.cg_dp_multimem_reason.restype = C.c_char_p
+        lib.cg_dp_set_multimem.restype, lib.cg_dp_set_multimem.argtypes = C.c_int, [C.c_int]
         lib.cg_grad.restype, lib.cg_grad.argtypes = C.c_void_p, [C.c_void_p, C.c_char_p]
         lib.cg_eval.restype = C.c_int
         lib.cg_eval.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(C.c_float)),
@@ -193,6 +198,28 @@ class ProductApi(Api):
     def dp_fused(self) -> bool:
         """True when weight gradients are exchanged by the fused peer-memory kernel rather than ncclAllReduce."""
         return bool(self.lib.cg_dp_fused())
+
+    def dp_multimem(self) -> bool:
+        """True when plans built now exchange weight gradients inside the NVSwitch (multimem.ld_reduce / multimem.st)."""
+        return bool(self.lib.cg_dp_multimem())
+
+    def dp_multimem_supported(self) -> bool:
+        return bool(self.lib.cg_dp_multimem_supported())
+
+    def dp_multimem_reason(self) -> str:
+        """Why the multicast heap could not be created (empty when it was)."""
+        return (self.lib.cg_dp_multimem_reason() or b"").decode()
+
+    def dp_set_multimem(self, mode: int):
+        """0 never, 1 (default) from three ranks up, 2 always."""
+        self._check(self.lib.cg_dp_set_multimem(int(mode)))
+
+    def dp_exchange_name(self) -> str:
+        if self.dp_multimem():
+            return "fused in-switch all-reduce + SGD update + broadcast kernel (NVLS multimem.ld_reduce / multimem.st over a symmetric multicast heap)"
+        if self.dp_fused():
+            return "fused all-reduce + SGD update kernel over NVLink peer memory (CUDA IPC)"
+        return "ncclAllReduce + elementwise update"
 
 
 def get_api() -> ProductApi:

@@ -94,10 +94,18 @@ int cg_minimize(cg_function* f, int nargs, const char** names, const float** arg
 }
 int cg_maximize(cg_function* f, int nargs, const char** names, const float** arg_vals, const unsigned* arg_h,
                 const unsigned* arg_w, float lr, int iters, int print_freq, float* trace) {
-  // optimize.rs:74-81: (-self).minimize(...)
+  // optimize.rs:74-81: (-self).minimize(...). The negated root shares f's body (and with it every leaf), so it is built
+  // once and kept on f: repeated calls reuse its compiled plan instead of re-planning (and re-compiling) each time.
   return guard_rc([&] {
-    std::unique_ptr<Function> n(make_unary(Kind::Neg, *F(f)));
-    minimize(*n, pack_args(nargs, names, arg_vals, arg_h, arg_w), lr, iters, print_freq, trace, true);
+    Function& fn = *F(f);
+    // (the constructor's value-based identity elimination, ops.rs:45-53, is re-decided per call as in the reference:
+    // `-f` IS `f` while f's cached value is all zeros)
+    const bool identity = value_all_equal(fn.value, 0.0f);
+    if (!fn.negated || fn.negated_identity != identity) {
+      fn.negated.reset(make_unary(Kind::Neg, fn));
+      fn.negated_identity = identity;
+    }
+    minimize(*fn.negated, pack_args(nargs, names, arg_vals, arg_h, arg_w), lr, iters, print_freq, trace, true);
   });
 }
 // optimize.rs:8-56: forward evaluation and the symbolic ("naive") gradient
@@ -186,8 +194,22 @@ void cg_set_mode(int m) { guard_rc([&] { Runtime::get().mode = m; }); }
 void cg_set_tf32(int v) { guard_rc([&] { Runtime::get().tf32 = v; }); }
 void cg_set_fix_act_grad(int v) { guard_rc([&] { Runtime::get().fix_act_grad = v; }); }
 void cg_set_fuse(int v) { guard_rc([&] { Runtime::get().fuse = v; }); }
-void cg_set_cuda_graph(int v) { guard_rc([&] { Runtime::get().use_graph = v; }); }
-void cg_set_strict_gemm_max(int v) { guard_rc([&] { Runtime::get().strict_gemm_max = v; }); }
+// (these three choices are baked into a compiled plan — its captured graphs, its kernel choice and its resident-executor
+// eligibility — so a change invalidates the cached plans, like every other setter below)
+void cg_set_cuda_graph(int v) {
+  guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    if (rt.use_graph != v) rt.dp_epoch++;
+    rt.use_graph = v;
+  });
+}
+void cg_set_strict_gemm_max(int v) {
+  guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    if (rt.strict_gemm_max != v) rt.dp_epoch++;
+    rt.strict_gemm_max = v;
+  });
+}
 void cg_set_ew_jit_min(long long v) { guard_rc([&] { Runtime::get().ew_jit_min = v; }); }
 int cg_ew_jit_available(void) { return ew_jit_available() ? 1 : 0; }
 // Compiles (NVRTC -> sm_100a cubin, no GPU needed) a program that uses every opcode; returns the cubin size or -1.
@@ -213,7 +235,13 @@ void cg_set_tf32_pair(int v) {
     Runtime::get().dp_epoch++;  // captured graphs hold the kernel choice: invalidate cached plans
   });
 }
-void cg_set_io_graph(int v) { guard_rc([&] { Runtime::get().io_graph = v; }); }
+void cg_set_io_graph(int v) {
+  guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    if (rt.io_graph != v) rt.dp_epoch++;
+    rt.io_graph = v;
+  });
+}
 int cg_set_plan_only(int on) {
   return guard_rc([&] {
     if (Runtime::get_if_initialised()) throw Error("cg_set_plan_only must be the first call into the library");
@@ -284,6 +312,7 @@ int cg_plan_stats_get(cg_function* f, float lr, cg_plan_stats* out) {
     out->tape_smem_bytes = s.tape_smem_bytes;
     out->quiet_variant = s.quiet_variant;
     out->quiet_ew_bytes_per_iter = s.quiet_ew_bytes_per_iter;
+    out->dp_multimem_updates = s.dp_multimem_updates;
   });
 }
 long long cg_plan_describe(cg_function* f, float lr, char* buf, unsigned long long cap) {
@@ -536,60 +565,3 @@ extern "C" int cg_profile_iteration(cg_function* f, float lr, double kind_ms[4],
     *max_gemm_count = best_cnt;
   });
 }
-
-// Bring-up probe: a tcgen05 product on one stream and an elementwise program on another, timed alone and
-// together (ms). Answers whether the two kernels become co-resident on an SM.
-extern "C" int cg_debug_overlap(double out_ms[3]) {
-  return guard_rc([&] {
-    Runtime& rt = Runtime::get();
-    const int B = 1024, H = 4096;
-    BufRef a = DevBuf::alloc((size_t)B * H), w = DevBuf::alloc((size_t)H * H), c = DevBuf::alloc((size_t)B * H);
-    BufRef e0 = DevBuf::alloc((size_t)H * H), e1 = DevBuf::alloc((size_t)H * H);
-    CG_CUDA(cudaMemset(a->ptr, 0, (size_t)B * H * 4));
-    CG_CUDA(cudaMemset(w->ptr, 0, (size_t)H * H * 4));
-    CG_CUDA(cudaMemset(e0->ptr, 0, (size_t)H * H * 4));
-    EwProgram p{};
-    p.n = (size_t)H * H;
-    p.n_in = 1, p.n_out = 1;
-    p.in[0] = e0->ptr, p.out[0] = e1->ptr;
-    int k = 0;
-    p.code[k++] = ew_encode(OP_LDR, 0);
-    p.code[k++] = ew_encode(OP_SIGMOID);
-    p.code[k++] = ew_encode(OP_TANH);
-    p.code[k++] = ew_encode(OP_SIGMOID);
-    p.code[k++] = ew_encode(OP_STG, 0);
-    p.n_ins = k;
-    cudaStream_t s1, s2;
-    CG_CUDA(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
-    CG_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-    cudaEvent_t ev[4];
-    for (auto& e : ev) CG_CUDA(cudaEventCreate(&e));
-    auto gem = [&](cudaStream_t s) {
-      for (int r = 0; r < 8; r++)
-        launch_gemm(a->ptr, false, w->ptr, false, c->ptr, B, H, H, B, H, B, GemmEpilogue{}, true, s);
-    };
-    auto eww = [&](cudaStream_t s) {
-      for (int r = 0; r < 2; r++) launch_ew_program(p, s);
-    };
-    for (int mode = 0; mode < 3; mode++) {
-      for (int rep = 0; rep < 2; rep++) {  // second repetition is the timed one
-        CG_CUDA(cudaDeviceSynchronize());
-        CG_CUDA(cudaEventRecord(ev[0], s1));
-        CG_CUDA(cudaStreamWaitEvent(s2, ev[0], 0));
-        if (mode == 0 || mode == 2) gem(s1);
-        if (mode == 1 || mode == 2) eww(s2);
-        CG_CUDA(cudaEventRecord(ev[1], s2));
-        CG_CUDA(cudaStreamWaitEvent(s1, ev[1], 0));
-        CG_CUDA(cudaEventRecord(ev[2], s1));
-        CG_CUDA(cudaEventSynchronize(ev[2]));
-        float ms = 0;
-        CG_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[2]));
-        out_ms[mode] = ms;
-      }
-    }
-    (void)rt;
-    cudaStreamDestroy(s1);
-    cudaStreamDestroy(s2);
-  });
-}
-

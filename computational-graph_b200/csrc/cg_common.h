@@ -147,7 +147,7 @@ constexpr int DP_MAX_WORLD = 8;
 constexpr int DP_THREADS = 512;
 constexpr int DP_DEFAULT_CTAS = 64;  // CG_DP_CTAS overrides
 int dp_max_ctas();
-constexpr unsigned long long DP_WAIT_TIMEOUT_NS = 4000000000ull;  // default 4 s (CG_DP_TIMEOUT_MS): a lost rank raises an error, never hangs the GPU
+constexpr unsigned long long DP_WAIT_TIMEOUT_NS = 20000000000ull;  // default 20 s (CG_DP_TIMEOUT_MS): a lost rank raises an error, never hangs the GPU
 enum { DP_FLAG_A = 0, DP_FLAG_B = 16, DP_FLAG_EPOCH = 32, DP_FLAG_TICKET = 33, DP_FLAG_ERR = 34, DP_FLAG_WORDS = 64 };
 struct DpReduceArgs {
   const float* g[DP_MAX_WORLD];  // the partial gradient in every rank (index = rank)
@@ -159,10 +159,38 @@ struct DpReduceArgs {
   unsigned long long timeout_ns;  // bound of every flag wait
 };
 void launch_dp_reduce_update(const DpReduceArgs& a, cudaStream_t stream);
+// The in-switch (NVLS multimem) form of the same exchange: buffers in the symmetric multicast heap (symm.cpp).
+struct DpMcArgs {
+  const float* g_mc;   // the gradient slot through the multicast object: a load sums it over every rank in the switch
+  const float* w_uc;   // this rank's weight, ordinary (unicast) address
+  float* w_mc;         // the weight through the multicast object: a store lands in every rank's copy
+  uint32_t* flags_uc;  // this rank's counter block (DP_FLAG_WORDS words, in the heap)
+  uint32_t* flags_mc;  // the same block through the multicast object
+  float lr;
+  size_t n;
+  int rank, world;
+  unsigned long long timeout_ns;
+};
+void launch_dp_multimem_update(const DpMcArgs& a, cudaStream_t stream);
+// Symmetric multicast heap (symm.cpp). symm_init / symm_alloc are collective over the data-parallel ranks.
+bool symm_init(unsigned long long job_id, int device_ordinal);
+void symm_shutdown();
+bool symm_available();
+const char* symm_unavailable_reason();
+void* symm_alloc(size_t bytes);
+void symm_free(void* uc);
+bool symm_locate(const void* uc, unsigned long long* seg, unsigned long long* off, void** mc);
+size_t symm_bytes_mapped();
+// Whether plans built now use the in-switch exchange (heap available and selected for this world size).
+bool dp_multimem_active();
+void dp_fill_mc_flags(DpMcArgs& a);
+std::vector<unsigned char> dp_allgather_bytes(const void* mine, size_t bytes);  // control messages over the communicator
 // Collective (every rank, same order): makes the cudaMalloc allocations that contain these pointers addressable from
 // every rank. Returns false when peer access is not available (plans then keep ncclAllReduce + a separate update).
 bool dp_register_windows(const std::vector<const void*>& ptrs);
-void dp_forget(const void* ptr, size_t bytes);  // a device buffer is about to be freed: drop its registrations
+// A device buffer is about to be freed: drops its registrations; true when dp.cpp has taken over the cudaFree (a peer
+// may still have the allocation open — it is freed at the next collective point).
+bool dp_retire(void* ptr, size_t bytes);
 size_t dp_fused_min_elems();  // weights smaller than this stay on ncclAllReduce (CG_DP_FUSED_MIN)
 // Fills the peer pointers for `local` (inside a registered window); false if it is not in one.
 bool dp_peer_pointers(const void* local, void* peers[DP_MAX_WORLD]);

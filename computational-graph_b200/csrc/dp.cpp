@@ -9,6 +9,10 @@
 // and hands the kernel the peer pointers and the flag blocks. ncclAllReduce remains for weights too small to be
 // worth a window, for machines without peer access and for CG_DP_FUSED=0.
 //
+// From three ranks up the exchange is done INSIDE the NVSwitch instead (NVLS multimem, dp_kernels.cu
+// dp_multimem_update_kernel): the gradient slots and the replicated weights of a plan then live in the symmetric
+// multicast heap of symm.cpp, which this file initialises next to the communicator.
+//
 // NCCL is resolved with dlopen at cg_dp_init time, so the library loads (and every single-GPU path
 // runs) on machines without NCCL, and a process that already carries torch's NCCL reuses that copy.
 #include <cuda.h>
@@ -78,14 +82,39 @@ std::vector<Opened> g_opened;
 std::vector<PeerMap> g_ptrs;
 std::vector<std::pair<char*, unsigned long long>> g_exported;  // this rank's allocations that peers may have open
 unsigned long long g_next_serial = 1;
+// Freeing an allocation that a peer still has open through cudaIpcOpenMemHandle is undefined behaviour, so a buffer that
+// was exported is not freed by its owner's destructor: it waits here until every peer has closed the mapping (the next
+// collective point: dp_register_windows or the shutdown).
+struct Retired {
+  void* ptr;                  // what cudaFree gets
+  char* base;                 // the allocation peers have open
+  unsigned long long serial;  // its export number
+};
+std::vector<Retired> g_graveyard;
+uint32_t* g_mc_flags = nullptr;     // counter block of the in-switch exchange (in the multicast heap)
+uint32_t* g_mc_flags_mc = nullptr;  // the same block through the multicast object
+int g_multimem_mode = 1;            // 0 never, 1 from three ranks up (fewer wire bytes than peer memory only there), 2 always
 uint32_t* g_flags = nullptr;  // this rank's flag block
 int g_fused = -1;             // -1 unknown, 0 unavailable (stay on ncclAllReduce), 1 available
 
+std::vector<unsigned char> allgather_bytes(const void* mine, size_t bytes);
+
+// Collective (every rank calls it at shutdown / re-initialisation).
 void close_windows() {
   for (Opened& o : g_opened) cudaIpcCloseMemHandle(o.base);
   g_opened.clear();
   g_ptrs.clear();
   g_exported.clear();
+  // nothing exported may be freed before every peer has closed it: one round over the communicator is the barrier
+  if (g_nccl.comm && g_nccl.world > 1 && (g_flags || !g_graveyard.empty())) {
+    unsigned long long one = 1;
+    try {
+      allgather_bytes(&one, sizeof one);
+    } catch (const std::exception&) {
+    }
+  }
+  for (Retired& r : g_graveyard) cudaFree(r.ptr);
+  g_graveyard.clear();
   if (g_flags) cudaFree(g_flags);
   g_flags = nullptr;
   g_fused = -1;
@@ -100,6 +129,7 @@ PeerMap* find_ptr(const void* p) {
 // all-gather of `bytes` host bytes per rank over the communicator
 std::vector<unsigned char> allgather_bytes(const void* mine, size_t bytes) {
   Runtime& rt = Runtime::get();
+  if (!g_nccl.comm) throw Error("internal: data-parallel control message without a communicator");
   unsigned char *send = nullptr, *recv = nullptr;
   CG_CUDA(cudaMalloc(&send, bytes));
   CG_CUDA(cudaMalloc(&recv, bytes * g_nccl.world));
@@ -142,12 +172,22 @@ char* allocation_base(const void* p) {
 
 }  // namespace
 
+std::vector<unsigned char> dp_allgather_bytes(const void* mine, size_t bytes) { return allgather_bytes(mine, bytes); }
+int dp_rank() { return g_nccl.rank; }
+int dp_world() { return g_nccl.world; }
+
 // plan-only mode (graph.cpp): a pretended world, so that the data-parallel tape can be inspected without GPUs
-static int g_plan_world = 1, g_plan_fused = 0;
+static int g_plan_world = 1, g_plan_fused = 0;  // g_plan_fused: 1 peer-memory exchange, 2 in-switch exchange
 
 bool dp_enabled() { return plan_only() ? g_plan_world > 1 : g_nccl.comm != nullptr && g_nccl.world > 1; }
 
-bool dp_fused_available() { return plan_only() ? g_plan_world > 1 && g_plan_fused : g_fused == 1; }
+bool dp_fused_available() { return plan_only() ? g_plan_world > 1 && g_plan_fused : (g_fused == 1 || dp_multimem_active()); }
+
+bool dp_multimem_active() {
+  if (plan_only()) return g_plan_world > 1 && g_plan_fused == 2;
+  if (!symm_available() || !g_mc_flags || g_multimem_mode == 0) return false;
+  return g_multimem_mode == 2 || g_nccl.world >= 3;
+}
 
 size_t dp_fused_min_elems() {
   static const size_t v = [] {
@@ -208,26 +248,61 @@ bool dp_register_windows(const std::vector<const void*>& ptrs) {
     pm[i].alloc = k;
     pm[i].offset = (unsigned long long)((const char*)todo[i] - base);
   }
+  // Allocations in the graveyard that no live registered buffer shares any more: their export numbers go to the peers,
+  // which close their mappings below; the memory is freed once everybody has.
+  std::vector<unsigned long long> retire;
+  for (const Retired& g : g_graveyard) {
+    bool shared = false;
+    for (const PeerMap& m : g_ptrs)
+      if (allocation_base(m.local) == g.base) shared = true;
+    for (const void* t : todo)
+      if (allocation_base(t) == g.base) shared = true;
+    if (!shared && std::find(retire.begin(), retire.end(), g.serial) == retire.end()) retire.push_back(g.serial);
+  }
   // Collective from here on. Ranks build identical plans, so they ask for the same number of buffers; if they ever
   // do not, every rank sees it in the gathered counts and all of them fall back together.
-  unsigned long long head[2] = {todo.size(), allocs.size()};
+  unsigned long long head[3] = {todo.size(), allocs.size(), retire.size()};
   std::vector<unsigned char> heads = allgather_bytes(head, sizeof head);
-  unsigned long long max_allocs = 0;
+  unsigned long long max_allocs = 0, max_retire = 0;
+  bool same_count = true;
   for (int r = 0; r < world; r++) {
-    unsigned long long h[2];
+    unsigned long long h[3];
     memcpy(h, heads.data() + r * sizeof h, sizeof h);
-    if (h[0] != head[0]) {
-      g_fused = 0;
-      return false;
-    }
+    if (h[0] != head[0]) same_count = false;
     max_allocs = std::max(max_allocs, h[1]);
+    max_retire = std::max(max_retire, h[2]);
   }
-  if (todo.empty()) return g_fused == 1;
-  const size_t blob_bytes = max_allocs * sizeof(AllocMsg) + todo.size() * sizeof(PtrMsg);
-  std::vector<unsigned char> blob(blob_bytes, 0);
-  memcpy(blob.data(), allocs.data(), allocs.size() * sizeof(AllocMsg));
-  memcpy(blob.data() + max_allocs * sizeof(AllocMsg), pm.data(), pm.size() * sizeof(PtrMsg));
-  std::vector<unsigned char> all = allgather_bytes(blob.data(), blob_bytes);
+  if (!same_count) {
+    g_fused = 0;
+    return false;
+  }
+  if (todo.empty() && max_retire == 0) return g_fused == 1;
+  const size_t retire_at = max_allocs * sizeof(AllocMsg) + todo.size() * sizeof(PtrMsg);
+  const size_t blob_bytes = retire_at + max_retire * sizeof(unsigned long long);
+  std::vector<unsigned char> blob(blob_bytes ? blob_bytes : 8, 0);
+  if (!allocs.empty()) memcpy(blob.data(), allocs.data(), allocs.size() * sizeof(AllocMsg));
+  if (!pm.empty()) memcpy(blob.data() + max_allocs * sizeof(AllocMsg), pm.data(), pm.size() * sizeof(PtrMsg));
+  if (!retire.empty()) memcpy(blob.data() + retire_at, retire.data(), retire.size() * sizeof(unsigned long long));
+  std::vector<unsigned char> all = allgather_bytes(blob.data(), blob.size());
+  const size_t blob_stride = blob.size();
+  // close what the peers have retired
+  for (int r = 0; r < world; r++) {
+    if (r == rank) continue;
+    unsigned long long h[3];
+    memcpy(h, heads.data() + r * sizeof h, sizeof h);
+    for (unsigned long long q = 0; q < h[2]; q++) {
+      unsigned long long serial;
+      memcpy(&serial, all.data() + (size_t)r * blob_stride + retire_at + q * sizeof serial, sizeof serial);
+      for (size_t k = 0; k < g_opened.size();) {
+        if (g_opened[k].rank == r && g_opened[k].serial == serial) {
+          cudaIpcCloseMemHandle(g_opened[k].base);
+          g_opened.erase(g_opened.begin() + k);
+        } else {
+          k++;
+        }
+      }
+    }
+  }
 
   int good = 1;
   std::vector<PeerMap> maps(todo.size());
@@ -239,10 +314,10 @@ bool dp_register_windows(const std::vector<const void*>& ptrs) {
   std::vector<Opened> fresh;
   for (int r = 0; r < world && good; r++) {
     if (r == rank) continue;
-    const unsigned char* rb = all.data() + (size_t)r * blob_bytes;
+    const unsigned char* rb = all.data() + (size_t)r * blob_stride;
     unsigned long long n_allocs_r;
     {
-      unsigned long long h[2];
+      unsigned long long h[3];
       memcpy(h, heads.data() + r * sizeof h, sizeof h);
       n_allocs_r = h[1];
     }
@@ -297,6 +372,18 @@ bool dp_register_windows(const std::vector<const void*>& ptrs) {
     memcpy(&o, outcomes.data() + r * sizeof o, sizeof o);
     if (!o) good = 0;
   }
+  // (the outcome round is also the barrier behind which every peer has closed what this rank retired)
+  for (size_t q = 0; q < g_graveyard.size();) {
+    if (std::find(retire.begin(), retire.end(), g_graveyard[q].serial) != retire.end()) {
+      for (size_t e = 0; e < g_exported.size();)
+        if (g_exported[e].second == g_graveyard[q].serial) g_exported.erase(g_exported.begin() + e);
+        else e++;
+      cudaFree(g_graveyard[q].ptr);
+      g_graveyard.erase(g_graveyard.begin() + q);
+    } else {
+      q++;
+    }
+  }
   if (!good) {
     for (Opened& o : fresh) cudaIpcCloseMemHandle(o.base);
     g_fused = 0;
@@ -304,12 +391,14 @@ bool dp_register_windows(const std::vector<const void*>& ptrs) {
   }
   for (Opened& o : fresh) g_opened.push_back(o);
   for (PeerMap& m : maps) g_ptrs.push_back(m);
-  g_fused = 1;
-  return true;
+  if (!todo.empty() || g_fused == -1) g_fused = 1;
+  return g_fused == 1;
 }
 
-void dp_forget(const void* ptr, size_t bytes) {
-  if (g_ptrs.empty() && g_exported.empty()) return;
+// A device buffer is about to be freed: drop its registrations. Returns true when this file has taken over the
+// cudaFree (the allocation was exported and a peer may still have it open).
+bool dp_retire(void* ptr, size_t bytes) {
+  if (g_ptrs.empty() && g_exported.empty()) return false;
   const char* lo = static_cast<const char*>(ptr);
   for (size_t q = 0; q < g_ptrs.size();) {
     const char* l = static_cast<const char*>(g_ptrs[q].local);
@@ -317,10 +406,13 @@ void dp_forget(const void* ptr, size_t bytes) {
     else q++;
   }
   char* base = allocation_base(ptr);
-  for (size_t q = 0; q < g_exported.size();) {
-    if (g_exported[q].first == base) g_exported.erase(g_exported.begin() + q);
-    else q++;
-  }
+  if (!base || !g_nccl.comm) return false;
+  for (const auto& e : g_exported)
+    if (e.first == base) {
+      g_graveyard.push_back(Retired{ptr, base, e.second});
+      return true;
+    }
+  return false;
 }
 
 bool dp_peer_pointers(const void* local, void* peers[DP_MAX_WORLD]) {
@@ -330,27 +422,43 @@ bool dp_peer_pointers(const void* local, void* peers[DP_MAX_WORLD]) {
   return true;
 }
 
+static unsigned long long dp_timeout_ns();
 void dp_fill_flags(DpReduceArgs& a) {
   void* peers[DP_MAX_WORLD];
   if (!g_flags || !dp_peer_pointers(g_flags, peers)) throw Error("internal: data-parallel flag window is not registered");
   for (int r = 0; r < DP_MAX_WORLD; r++) a.flags[r] = static_cast<uint32_t*>(peers[r]);
   a.rank = g_nccl.rank;
   a.world = g_nccl.world;
+  a.timeout_ns = dp_timeout_ns();
+}
+
+static unsigned long long dp_timeout_ns() {
   static const unsigned long long timeout_ns = [] {
     const char* e = getenv("CG_DP_TIMEOUT_MS");  // how long an exchange waits for a peer before it reports a lost rank
     const long long ms = e ? atoll(e) : 0;
     return ms > 0 ? (unsigned long long)ms * 1000000ull : DP_WAIT_TIMEOUT_NS;
   }();
-  a.timeout_ns = timeout_ns;
+  return timeout_ns;
+}
+
+void dp_fill_mc_flags(DpMcArgs& a) {
+  if (!g_mc_flags) throw Error("internal: the in-switch exchange has no counter block");
+  a.flags_uc = g_mc_flags;
+  a.flags_mc = g_mc_flags_mc;
+  a.rank = g_nccl.rank;
+  a.world = g_nccl.world;
+  a.timeout_ns = dp_timeout_ns();
 }
 
 void dp_check_errors() {
-  if (!g_flags) return;
-  uint32_t err = 0;
-  CG_CUDA(cudaMemcpy(&err, g_flags + DP_FLAG_ERR, sizeof err, cudaMemcpyDeviceToHost));
-  if (err) {
-    CG_CUDA(cudaMemset(g_flags + DP_FLAG_ERR, 0, sizeof err));
-    throw Error("data-parallel exchange timed out waiting for a peer rank (ranks must run the same iterations in the same order)");
+  for (uint32_t* flags : {g_flags, g_mc_flags}) {
+    if (!flags) continue;
+    uint32_t err = 0;
+    CG_CUDA(cudaMemcpy(&err, flags + DP_FLAG_ERR, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) {
+      CG_CUDA(cudaMemset(flags + DP_FLAG_ERR, 0, sizeof err));
+      throw Error("data-parallel exchange timed out waiting for a peer rank (ranks must run the same iterations in the same order)");
+    }
   }
 }
 
@@ -387,6 +495,8 @@ int cg_dp_init(int rank, int world, const unsigned char id[CG_DP_ID_BYTES]) {
       CG_CUDA(cudaStreamSynchronize(rt.stream));
       release_all_plan_graphs();
       close_windows();
+      symm_shutdown();
+      g_mc_flags = g_mc_flags_mc = nullptr;
       g_nccl.CommDestroy(g_nccl.comm);
       g_nccl.comm = nullptr;
     }
@@ -399,6 +509,25 @@ int cg_dp_init(int rank, int world, const unsigned char id[CG_DP_ID_BYTES]) {
     // Decide once, together, whether the ranks can address each other's memory (CUDA IPC over NVLink): opens the
     // flag blocks. Plans built from here on use the fused exchange kernel when they can, ncclAllReduce otherwise.
     if (world > 1) dp_register_windows({});
+    // ... and whether the NVSwitch can do the summing (multicast objects over VMM memory, symm.cpp). The job id that
+    // names the ranks' unix sockets is a hash of the NCCL unique id: the same on every rank, different per job.
+    g_mc_flags = g_mc_flags_mc = nullptr;
+    if (world > 1 && world <= DP_MAX_WORLD) {
+      unsigned long long job = 1469598103934665603ull;
+      for (int k = 0; k < CG_DP_ID_BYTES; k++) job = (job ^ id[k]) * 1099511628211ull;
+      int dev = 0;
+      CG_CUDA(cudaGetDevice(&dev));
+      if (symm_init(job, dev)) {
+        g_mc_flags = static_cast<uint32_t*>(symm_alloc(4096));
+        void* mc = nullptr;
+        symm_locate(g_mc_flags, nullptr, nullptr, &mc);
+        g_mc_flags_mc = static_cast<uint32_t*>(mc);
+        CG_CUDA(cudaMemset(g_mc_flags, 0, 4096));
+        CG_CUDA(cudaDeviceSynchronize());
+        unsigned long long one = 1;
+        allgather_bytes(&one, sizeof one);  // every rank's counters are zero before anybody's kernel adds to them
+      }
+    }
     // NCCL's all-reduce kernels need SMs of their own to overlap the products of the backward pass, so the persistent
     // product grid leaves some free; the fused exchange kernel is sized to sit BESIDE a product CTA on the same SM
     // (dp_kernels.cu), so nothing is reserved for it.
@@ -411,6 +540,19 @@ int cg_dp_init(int rank, int world, const unsigned char id[CG_DP_ID_BYTES]) {
   }
 }
 int cg_dp_fused(void) { return dp_fused_available() ? 1 : 0; }
+int cg_dp_multimem(void) { return dp_multimem_active() ? 1 : 0; }
+int cg_dp_multimem_supported(void) { return symm_available() ? 1 : 0; }
+const char* cg_dp_multimem_reason(void) { return symm_unavailable_reason(); }
+int cg_dp_set_multimem(int mode) {
+  try {
+    if (mode < 0 || mode > 2) throw Error("cg_dp_set_multimem: mode must be 0 (never), 1 (from three ranks up) or 2 (always)");
+    if (g_multimem_mode != mode) Runtime::get().dp_epoch++;  // the exchange kernel is part of a compiled plan
+    g_multimem_mode = mode;
+    return 0;
+  } catch (const std::exception& e) {
+    return cg_dp_set_error(e.what());
+  }
+}
 int cg_dp_plan_only(int world, int fused) {
   try {
     if (!plan_only()) throw Error("cg_dp_plan_only is only available in plan-only mode (cg_set_plan_only)");
@@ -428,6 +570,12 @@ int cg_dp_shutdown(void) {
       CG_CUDA(cudaStreamSynchronize(Runtime::get().stream));
       release_all_plan_graphs();  // captured all-reduces pin the communicator: ncclCommDestroy would never return
       close_windows();
+      {
+        unsigned long long one = 1;
+        allgather_bytes(&one, sizeof one);  // nobody unmaps its part of the multicast heap under a peer's last exchange
+      }
+      symm_shutdown();
+      g_mc_flags = g_mc_flags_mc = nullptr;
       g_nccl.CommDestroy(g_nccl.comm);
       g_nccl.comm = nullptr;
       g_nccl.world = 1;

@@ -83,11 +83,16 @@ __global__ void __launch_bounds__(DP_THREADS, 2) dp_reduce_update_kernel(const D
   // ---- barrier A: every rank's partial gradient is complete, and every rank is done reading the old weight ----
   if (blockIdx.x == 0 && (int)threadIdx.x < WORLD) st_release_sys(a.flags[threadIdx.x] + DP_FLAG_A + a.rank, epoch);
   wait_all(own, DP_FLAG_A, WORLD, epoch, own + DP_FLAG_ERR, a.timeout_ns);
+  // A peer that never arrived: its gradient is not there to be summed. Leave W alone (the host raises the error at its
+  // next synchronisation) but keep the ticket / epoch bookkeeping below going so that later kernels drain.
+  __shared__ bool s_lost;
+  if (threadIdx.x == 0) s_lost = ld_acquire_sys(own + DP_FLAG_ERR) != 0;
+  __syncthreads();
 
   // ---- this rank's slice: sum over ranks in rank order, update once, store everywhere -------------------------
   const size_t n4 = a.n / 4;  // the caller guarantees n % 4 == 0 and 16-byte aligned buffers
   const size_t per = (n4 + WORLD - 1) / WORLD;
-  const size_t lo = (size_t)a.rank * per, hi = lo + per < n4 ? lo + per : n4;
+  const size_t lo = (size_t)a.rank * per, hi = s_lost ? 0 : (lo + per < n4 ? lo + per : n4);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i0 = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * UNROLL) {
     float4 g[WORLD][UNROLL], w[UNROLL];
@@ -140,6 +145,111 @@ __global__ void __launch_bounds__(DP_THREADS, 2) dp_reduce_update_kernel(const D
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same exchange with the sum done INSIDE the NVSwitch (NVLS): the gradient slot and the weight live in the symmetric
+// multicast heap (symm.cpp), so for its 1/world slice a rank issues ONE multimem.ld_reduce per 16 bytes — the switch
+// pulls the four floats from every GPU, adds them and returns the sum — applies W <- W - (sum * lr) (two roundings,
+// optimize.rs:149-152) and issues ONE multimem.st that the switch replicates into every GPU's W. Per GPU and direction
+// that is (1 + 1/world) n bytes on the wire instead of the 2 (world-1)/world n of the peer-memory kernel above: 1.125 n
+// vs 1.75 n at 8 ranks (it is MORE at 2 ranks: 1.5 n vs n, which is why dp.cpp only selects it from 3 ranks up). Every
+// element is summed once, by the switch, and broadcast, so the replicas stay bit-identical to each other; the order of
+// the switch's f32 additions is the hardware's, which the 1e-5 / 1e-3 data-parallel tolerance of SURVEY §8e covers.
+//
+// Barriers: one multimem.red.add on a counter that exists on every GPU is "I have arrived" on all of them at once; a rank
+// waits until its own copy reads epoch * world. The multicast address aliases the unicast one, hence fence.proxy.alias
+// between the reduction and the polling loads.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mc_signal(uint32_t* mc_counter) {
+  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_counter), "r"(1u) : "memory");
+  asm volatile("fence.proxy.alias;" ::: "memory");
+}
+__device__ __forceinline__ float4 mc_ld_reduce(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// thread 0 of the CTA polls this rank's counter until it reaches `target` (wrap-safe), bounded like wait_all
+__device__ __forceinline__ void mc_wait(const uint32_t* counter, uint32_t target, uint32_t* err, unsigned long long timeout_ns) {
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(counter) - target) < 0) {
+      if (ld_acquire_sys(err) != 0) break;
+      if (global_ns() - t0 > timeout_ns) {
+        st_release_sys(err, 1u);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(DP_THREADS, 2) dp_multimem_update_kernel(const DpMcArgs a) {
+  __shared__ uint32_t s_epoch;
+  __shared__ bool s_last, s_lost;
+  uint32_t* own = a.flags_uc;
+  if (threadIdx.x == 0) s_epoch = own[DP_FLAG_EPOCH] + 1;
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  const uint32_t target = epoch * (uint32_t)a.world;
+
+  // ---- barrier A: every rank's partial gradient is complete, and every rank is done reading the old weight ----
+  if (blockIdx.x == 0 && threadIdx.x == 0) mc_signal(a.flags_mc + DP_FLAG_A);
+  mc_wait(own + DP_FLAG_A, target, own + DP_FLAG_ERR, a.timeout_ns);
+  if (threadIdx.x == 0) s_lost = ld_acquire_sys(own + DP_FLAG_ERR) != 0;
+  __syncthreads();
+
+  // ---- this rank's slice: in-switch sum, one update, in-switch broadcast ---------------------------------------
+  const size_t n4 = a.n / 4;
+  const size_t per = (n4 + a.world - 1) / a.world;
+  const size_t lo = (size_t)a.rank * per, hi = s_lost ? 0 : (lo + per < n4 ? lo + per : n4);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * UNROLL) {
+    float4 g[UNROLL], w[UNROLL];
+    bool ok[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) ok[u] = i0 + (size_t)u * stride < hi;
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++)
+      if (ok[u]) g[u] = mc_ld_reduce(a.g_mc + (i0 + (size_t)u * stride) * 4);
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++)
+      if (ok[u]) w[u] = ld_stream(a.w_uc + (i0 + (size_t)u * stride) * 4);
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      if (!ok[u]) continue;
+      float4 o;
+      o.x = __fsub_rn(w[u].x, __fmul_rn(g[u].x, a.lr));
+      o.y = __fsub_rn(w[u].y, __fmul_rn(g[u].y, a.lr));
+      o.z = __fsub_rn(w[u].z, __fmul_rn(g[u].z, a.lr));
+      o.w = __fsub_rn(w[u].w, __fmul_rn(g[u].w, a.lr));
+      mc_st(a.w_mc + (i0 + (size_t)u * stride) * 4, o);
+    }
+  }
+
+  // ---- barrier B: the last CTA of this rank signals, and waits for, the end of every rank's traffic ------------
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(own + DP_FLAG_TICKET, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) mc_signal(a.flags_mc + DP_FLAG_B);
+  mc_wait(own + DP_FLAG_B, target, own + DP_FLAG_ERR, a.timeout_ns);
+  if (threadIdx.x == 0) {
+    own[DP_FLAG_TICKET] = 0;
+    own[DP_FLAG_EPOCH] = epoch;
+    __threadfence();
+  }
+}
+
 template <int WORLD, int UNROLL>
 void launch_world(const DpReduceArgs& a, cudaStream_t stream) {
   const size_t slice4 = (a.n / 4 + WORLD - 1) / WORLD;
@@ -158,6 +268,21 @@ int dp_max_ctas() {
     return n < 1 ? 1 : n > kNumSMs ? kNumSMs : n;
   }();
   return v;
+}
+
+void launch_dp_multimem_update(const DpMcArgs& a, cudaStream_t stream) {
+  if (a.n == 0) return;
+  if (a.n % 4) throw Error("internal: fused data-parallel update needs a multiple of 4 elements");
+  // The switch does the summing, so few threads keep the link busy: a rank only PULLS n / world bytes (the rest of its
+  // inbound traffic is its peers' posted multicast stores). Two loads per thread from 3 ranks on, four at 2 ranks.
+  const size_t slice4 = (a.n / 4 + a.world - 1) / a.world;
+  const int unroll = a.world <= 2 ? 4 : 2;
+  size_t grid = (slice4 + (size_t)DP_THREADS * unroll - 1) / ((size_t)DP_THREADS * unroll);
+  if (grid > (size_t)dp_max_ctas()) grid = dp_max_ctas();
+  if (grid < 1) grid = 1;
+  if (unroll == 4) dp_multimem_update_kernel<4><<<(unsigned)grid, DP_THREADS, 0, stream>>>(a);
+  else dp_multimem_update_kernel<2><<<(unsigned)grid, DP_THREADS, 0, stream>>>(a);
+  CG_CUDA(cudaGetLastError());
 }
 
 void launch_dp_reduce_update(const DpReduceArgs& a, cudaStream_t stream) {

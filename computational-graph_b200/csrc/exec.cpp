@@ -1,6 +1,5 @@
 // exec.cpp — `minimize` (src/optimize.rs:59-72) over a compiled plan: one CUDA-graph replay per iteration.
 #include <algorithm>
-#include <chrono>
 #include <cstring>
 #include <functional>
 #include <unordered_map>
@@ -83,17 +82,12 @@ struct Loc {
 constexpr int kIoLanes = 4;
 
 void capture_nodes(Plan& p, Runtime& rt, std::vector<CapNode>& nodes, cudaGraph_t* graph_out, cudaGraphExec_t* exec_out) {
-  const int nstreams = rt.graph_streams > 0 ? rt.graph_streams : 0;
+  const int nstreams = rt.graph_streams > 0 ? rt.graph_streams : 0;  // (only the copy lane of launch_io_graph is a real stream)
   const size_t n = nodes.size();
   if ((int)rt.side_streams.size() < nstreams + kIoLanes) {
     rt.side_streams.resize(nstreams + kIoLanes, nullptr);
     for (auto& st : rt.side_streams)
       if (!st) CG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  }
-  while (p.events.size() < n + 1) {
-    cudaEvent_t e;
-    CG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    p.events.push_back(e);
   }
   // dependencies from memory locations (RAW, WAR, WAW), in program order
   std::unordered_map<const float*, Loc> loc;
@@ -116,11 +110,7 @@ void capture_nodes(Plan& p, Runtime& rt, std::vector<CapNode>& nodes, cudaGraph_
       l.readers.clear();
     }
   }
-  static const bool exact_dag = [] {
-    const char* e = getenv("CG_GRAPH_EXACT");
-    return !e || atoi(e) != 0;
-  }();
-  if (exact_dag) {
+  {
     // Exact DAG: everything is captured on ONE stream whose capture dependency set is replaced, before every node,
     // by exactly the nodes that node depends on (cudaStreamUpdateCaptureDependencies). No stream-order edges exist, so
     // a kernel that waits for a late input can never hold back an unrelated kernel that happened to be captured
@@ -168,60 +158,7 @@ void capture_nodes(Plan& p, Runtime& rt, std::vector<CapNode>& nodes, cudaGraph_
     }
     CG_CUDA(cudaStreamEndCapture(rt.stream, graph_out));
     CG_CUDA(cudaGraphInstantiate(exec_out, *graph_out, 0));
-    return;
   }
-  // streams: [0] the capturing (origin) stream, [1, nstreams] compute side streams, then the transfer lanes
-  std::vector<cudaStream_t> streams{rt.stream};
-  for (int k = 0; k < nstreams + kIoLanes; k++) streams.push_back(rt.side_streams[k]);
-  const size_t ncompute = (size_t)nstreams + 1;
-  std::vector<int> stream_last(streams.size(), -1), node_stream(n, 0);
-  std::vector<char> forked(streams.size(), 0);
-  forked[0] = 1;
-  cudaEvent_t fork_ev = p.events[n];
-  CG_CUDA(cudaStreamBeginCapture(rt.stream, cudaStreamCaptureModeThreadLocal));
-  try {
-    CG_CUDA(cudaEventRecord(fork_ev, rt.stream));
-    for (size_t i = 0; i < n; i++) {
-      int chosen = -1;
-      if (nodes[i].lane >= 0) {
-        chosen = (int)ncompute + nodes[i].lane;
-      } else {
-        // 1. a stream whose most recent node is one of our dependencies: no extra edge, no false dependency
-        for (size_t s = 0; s < ncompute; s++)
-          if (stream_last[s] >= 0 && std::find(deps[i].begin(), deps[i].end(), stream_last[s]) != deps[i].end())
-            if (chosen < 0 || stream_last[s] > stream_last[chosen]) chosen = (int)s;
-        // 2. an unused stream; 3. the stream that has been idle longest
-        if (chosen < 0)
-          for (size_t s = 0; s < ncompute && chosen < 0; s++)
-            if (stream_last[s] < 0) chosen = (int)s;
-        if (chosen < 0) {
-          chosen = 0;
-          for (size_t s = 1; s < ncompute; s++)
-            if (stream_last[s] < stream_last[chosen]) chosen = (int)s;
-        }
-      }
-      cudaStream_t st = streams[chosen];
-      if (!forked[chosen]) {
-        CG_CUDA(cudaStreamWaitEvent(st, fork_ev, 0));
-        forked[chosen] = 1;
-      }
-      for (int d : deps[i])
-        if (node_stream[d] != chosen) CG_CUDA(cudaStreamWaitEvent(st, p.events[d], 0));
-      nodes[i].launch(st);
-      CG_CUDA(cudaEventRecord(p.events[i], st));
-      stream_last[chosen] = (int)i;
-      node_stream[i] = chosen;
-    }
-    for (size_t s = 1; s < streams.size(); s++)
-      if (stream_last[s] >= 0) CG_CUDA(cudaStreamWaitEvent(rt.stream, p.events[stream_last[s]], 0));
-  } catch (...) {
-    cudaGraph_t g = nullptr;
-    cudaStreamEndCapture(rt.stream, &g);
-    if (g) cudaGraphDestroy(g);
-    throw;
-  }
-  CG_CUDA(cudaStreamEndCapture(rt.stream, graph_out));
-  CG_CUDA(cudaGraphInstantiate(exec_out, *graph_out, 0));
 }
 
 void capture_dag(Plan& p, Runtime& rt) {
@@ -411,26 +348,9 @@ void launch_io_graph(Plan& p, Runtime& rt, const std::vector<Arg>& args, float* 
     if (!p.io_done) CG_CUDA(cudaEventCreateWithFlags(&p.io_done, cudaEventDisableTiming));
     CG_CUDA(cudaEventRecord(p.io_done, rt.stream));
     CG_CUDA(cudaStreamWaitEvent(copy, p.io_done, 0));
-    static const bool dbg = getenv("CG_DEBUG_TIMING") != nullptr;
-    static cudaEvent_t t0 = nullptr, t1 = nullptr;
-    if (dbg && !t0) {
-      cudaEventCreate(&t0);
-      cudaEventCreate(&t1);
-    }
-    if (dbg) cudaEventRecord(t0, copy);
     for (size_t i : g.order) {
       CG_CUDA(cudaMemcpyAsync(g.h2d_dst[i], src[i], g.h2d_bytes[i], cudaMemcpyHostToDevice, copy));
       CG_CUDA(cudaEventRecord(g.in_ev[i], copy));
-    }
-    if (dbg) {
-      cudaEventRecord(t1, copy);
-      CG_CUDA(cudaGraphLaunch(g.exec, rt.stream));
-      rt.launches += p.steps.size() + g.layout_kernels;
-      cudaEventSynchronize(t1);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, t0, t1);
-      fprintf(stderr, "[cg timing] copy stream: %zu H2D copies took %.3f ms next to the iteration\n", nin, ms);
-      return;
     }
   }
   CG_CUDA(cudaGraphLaunch(g.exec, rt.stream));
@@ -490,21 +410,10 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
     if (iters > 0) throw Error("plan-only mode: minimize needs a CUDA device (this backend has no CPU path)");
     return;  // the plan is compiled; nothing is captured or launched
   }
-  static const bool dbg = getenv("CG_DEBUG_TIMING") != nullptr;
-  cudaEvent_t dbg_ev[3] = {};
-  double dbg_t0 = 0;
-  auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  if (dbg) {
-    for (auto& e : dbg_ev) cudaEventCreate(&e);
-    dbg_t0 = wall();
-    cudaEventRecord(dbg_ev[0], rt.stream);
-  }
   // One iteration whose host transfers ride inside the graph (pinned buffers only); otherwise: upload, then loop.
   const bool vm = p.vm_steps != nullptr || p.tape_kernel != nullptr;
   const bool io = !vm && !reuse_inputs && iters >= 1 && (iters == 1 || !trace) && io_graph_eligible(p, rt, args, trace);
   if (!reuse_inputs && !io) upload_inputs(p, args);
-  if (dbg) cudaEventRecord(dbg_ev[1], rt.stream);
-  const double dbg_t1 = dbg ? wall() : 0;
   for (Function* leaf : p.param_leaves) leaf->value.summary_valid = false;  // device values diverge from here on
   f.value.summary_valid = false;
   f.value.defined = true;
@@ -573,20 +482,9 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
     CG_CUDA(cudaStreamSynchronize(rt.stream));
     CG_CUDA(cudaFree(trace_dev));
   }
-  const double dbg_t2 = dbg ? wall() : 0;
   if (synchronize) CG_CUDA(cudaStreamSynchronize(rt.stream));
   // a fused data-parallel exchange that lost a peer records it instead of hanging the GPU: raise it here
   if ((synchronize || trace) && p.stats.dp_fused_updates) dp_check_errors();
-  if (dbg) {
-    cudaEventRecord(dbg_ev[2], rt.stream);
-    cudaEventSynchronize(dbg_ev[2]);
-    float up = 0, run = 0;
-    cudaEventElapsedTime(&up, dbg_ev[0], dbg_ev[1]);
-    cudaEventElapsedTime(&run, dbg_ev[1], dbg_ev[2]);
-    fprintf(stderr, "[cg timing] io=%d iters=%d host: upload-enqueue %.3f ms, loop-enqueue %.3f ms, sync %.3f ms | device: upload %.3f ms, loop %.3f ms\n",
-            (int)io, iters, dbg_t1 - dbg_t0, dbg_t2 - dbg_t1, wall() - dbg_t2, up, run);
-    for (auto& e : dbg_ev) cudaEventDestroy(e);
-  }
 }
 
 }  // namespace cg

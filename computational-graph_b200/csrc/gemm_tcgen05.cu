@@ -125,22 +125,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // does not wait for a whole persistent product to drain before it can start.
 int g_max_ctas = kNumSMs;
 
-struct TuneParams {
-  // descriptor strides; defaults follow the canonical layouts, overridable from the environment for bring-up
-  uint32_t k_lbo, k_sbo, k_step;     // K-major operand
-  uint32_t mn_lbo, mn_sbo, mn_step;  // MN-major operand
-  uint32_t mn_layout;                // descriptor layout type of the MN-major operand
-  uint32_t mn_chunked;               // 1: fetch MN-major tiles as 2-D boxes {32, BK}, one per 32-wide chunk
-  uint32_t pair_peer_arrives;        // pair kernel: the peer's producer also arrives on the leader's full barrier
-  uint32_t pair_small_only;          // pair kernel bring-up: fetch B in small boxes only
-  uint32_t debug_clock;              // block 0 prints SM cycles / nanoseconds spent in its main loop (clock under load)
-};
+// Shared-memory descriptor strides of the two canonical operand layouts (bytes).
+constexpr uint32_t K_LBO = 16, K_SBO = 1024, K_STEP = UMMA_K * 4;   // K-major: 8-row atoms 1024 B apart; +32 B per K step
+constexpr uint32_t MN_LBO = BK * 128, MN_SBO = 512, MN_STEP = 1024;  // MN-major: 32-wide chunks 4096 B apart; 4-row atoms; +8 k-rows per step
+constexpr uint32_t MN_LAYOUT = 1;                                    // SWIZZLE_128B_BASE32B
 
 template <int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     float* __restrict__ C, int m, int n, int k, int ldc, int epi_mode, float lr, TuneParams tp) {
-  // tp.mn_chunked: the MN-major tile is fetched as ROWS/32 two-dimensional boxes instead of one 3-D box
+                     float* __restrict__ C, int m, int n, int k, int ldc, int epi_mode, float lr) {
   constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 512 or 256: a power of two >= 32
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -189,24 +182,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          if (A_MN) {
-            if (tp.mn_chunked) {
-              for (int c = 0; c < BM / 32; c++) tma_load_2d(sa + c * (BK * 128), &map_a, &full_bar[stage], m0 + c * 32, kb * BK);
-            } else {
-              tma_load_3d(sa, &map_a, &full_bar[stage], 0, kb * BK, m0 / 32);
-            }
-          } else {
-            tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m0);
-          }
-          if (B_MN) {
-            if (tp.mn_chunked) {
-              for (int c = 0; c < BN / 32; c++) tma_load_2d(sb + c * (BK * 128), &map_b, &full_bar[stage], n0 + c * 32, kb * BK);
-            } else {
-              tma_load_3d(sb, &map_b, &full_bar[stage], 0, kb * BK, n0 / 32);
-            }
-          } else {
-            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n0);
-          }
+          if (A_MN) tma_load_3d(sa, &map_a, &full_bar[stage], 0, kb * BK, m0 / 32);
+          else tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m0);
+          if (B_MN) tma_load_3d(sb, &map_b, &full_bar[stage], 0, kb * BK, n0 / 32);
+          else tma_load_2d(sb, &map_b, &full_bar[stage], kb * BK, n0);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
@@ -218,11 +197,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      long long c0 = 0, t0 = 0;
-      if (tp.debug_clock && blockIdx.x == 0) {
-        c0 = clock64();
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
@@ -233,10 +207,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; kk++) {
-            const uint64_t da = A_MN ? make_smem_desc(sa + kk * tp.mn_step, tp.mn_lbo, tp.mn_sbo, tp.mn_layout)
-                                     : make_smem_desc(sa + kk * tp.k_step, tp.k_lbo, tp.k_sbo, 2);
-            const uint64_t db = B_MN ? make_smem_desc(sb + kk * tp.mn_step, tp.mn_lbo, tp.mn_sbo, tp.mn_layout)
-                                     : make_smem_desc(sb + kk * tp.k_step, tp.k_lbo, tp.k_sbo, 2);
+            const uint64_t da = A_MN ? make_smem_desc(sa + kk * MN_STEP, MN_LBO, MN_SBO, MN_LAYOUT)
+                                     : make_smem_desc(sa + kk * K_STEP, K_LBO, K_SBO, 2);
+            const uint64_t db = B_MN ? make_smem_desc(sb + kk * MN_STEP, MN_LBO, MN_SBO, MN_LAYOUT)
+                                     : make_smem_desc(sb + kk * K_STEP, K_LBO, K_SBO, 2);
             tcgen05_mma_tf32(tmem_d, da, db, idesc, (kb | kk) != 0);
           }
           tcgen05_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
@@ -244,12 +218,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         tcgen05_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
-      }
-      if (tp.debug_clock && blockIdx.x == 0) {
-        long long c1 = clock64(), t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        printf("[gemm_tf32 clock] issue loop: %lld cycles in %lld ns = %.0f MHz (k-blocks %d)\n", c1 - c0, t1 - t0,
-               (double)(c1 - c0) * 1e3 / (double)(t1 - t0), num_kb);
       }
     }
   } else {
@@ -396,7 +364,7 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_big,
                           const __grid_constant__ CUtensorMap map_b_small, float* __restrict__ C, int m, int n, int k, int ldc,
-                          int epi_mode, float lr, TuneParams tp, int cols_per_pair, int wmax) {
+                          int epi_mode, float lr, int wmax) {
   // B arrives in one box of wmax / 2 columns for a full-width chunk, in 16-row (K-major) / 32-column (MN-major) boxes for
   // the partial chunks at the ends of a range: TMA issue cost is per instruction, so the common case must be one box.
   constexpr int SMALL = B_MN ? 32 : 16;
@@ -420,7 +388,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_big) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_small) : "memory");
     for (int s = 0; s < STAGES2; s++) {
-      mbar_init(&full_bar[s], tp.pair_peer_arrives ? 2 : 1);
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < ACC_STAGES; s++) {
@@ -459,15 +427,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           else tma2_load_2d(sa, &map_a, lbar, kb * BK, m0);
           int done = 0;
           if (B_MN) {
-            for (; done + BIG <= half && !tp.pair_small_only; done += BIG) tma2_load_3d(sb + done * 128, &map_b_big, lbar, 0, kb * BK, (b0 + done) / 32);
+            for (; done + BIG <= half; done += BIG) tma2_load_3d(sb + done * 128, &map_b_big, lbar, 0, kb * BK, (b0 + done) / 32);
             for (; done < half; done += SMALL) tma2_load_3d(sb + done * 128, &map_b_small, lbar, 0, kb * BK, (b0 + done) / 32);
           } else {
-            for (; done + BIG <= half && !tp.pair_small_only; done += BIG) tma2_load_2d(sb + done * 128, &map_b_big, lbar, kb * BK, b0 + done);
+            for (; done + BIG <= half; done += BIG) tma2_load_2d(sb + done * 128, &map_b_big, lbar, kb * BK, b0 + done);
             for (; done < half; done += SMALL) tma2_load_2d(sb + done * 128, &map_b_small, lbar, kb * BK, b0 + done);
           }
           // the leader accounts for the bytes of both CTAs (its single arrival + 2 x bytes complete the phase)
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * bytes);
-          else if (tp.pair_peer_arrives) mbar_arrive_cluster(lbar);
           if (++stage == STAGES2) stage = 0, phase ^= 1;
         }
       }
@@ -491,10 +458,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES2), sb = sa + A_BYTES2;
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; kk++) {
-            const uint64_t da = A_MN ? make_smem_desc(sa + kk * tp.mn_step, tp.mn_lbo, tp.mn_sbo, tp.mn_layout)
-                                     : make_smem_desc(sa + kk * tp.k_step, tp.k_lbo, tp.k_sbo, 2);
-            const uint64_t db = B_MN ? make_smem_desc(sb + kk * tp.mn_step, tp.mn_lbo, tp.mn_sbo, tp.mn_layout)
-                                     : make_smem_desc(sb + kk * tp.k_step, tp.k_lbo, tp.k_sbo, 2);
+            const uint64_t da = A_MN ? make_smem_desc(sa + kk * MN_STEP, MN_LBO, MN_SBO, MN_LAYOUT)
+                                     : make_smem_desc(sa + kk * K_STEP, K_LBO, K_SBO, 2);
+            const uint64_t db = B_MN ? make_smem_desc(sb + kk * MN_STEP, MN_LBO, MN_SBO, MN_LAYOUT)
+                                     : make_smem_desc(sb + kk * K_STEP, K_LBO, K_SBO, 2);
             tcgen05_mma_tf32_pair(tmem_d, da, db, idesc, (kb | kk) != 0);
           }
           tcgen05_commit_pair(&empty_bar[stage]);  // frees the slot in BOTH CTAs once these MMAs have read it
@@ -576,14 +543,11 @@ void resolve_encode() {
   if (!g_encode) throw Error("cuTensorMapEncodeTiled is not available from this driver");
 }
 
-CUtensorMapSwizzle mn_swizzle() {
-  if (const char* e = getenv("CG_TF32_MN_TMA_SWIZZLE")) return (CUtensorMapSwizzle)atoi(e);
-  return CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-}
+constexpr CUtensorMapSwizzle MN_TMA_SWIZZLE = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
 
 // Tensor map of one operand tile. `mn` = extent along M (A) or N (B); `kdim` = contraction extent;
 // `ld` = stored leading dimension (floats); rows = tile extent along mn.
-CUtensorMap make_operand_map(const float* base, bool mn_major, int mn, int kdim, int ld, int rows, bool chunked) {
+CUtensorMap make_operand_map(const float* base, bool mn_major, int mn, int kdim, int ld, int rows) {
   resolve_encode();
   CUtensorMap map;
   CUresult r;
@@ -596,14 +560,6 @@ CUtensorMap make_operand_map(const float* base, bool mn_major, int mn, int kdim,
     r = g_encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  } else if (chunked) {
-    cuuint64_t dims[2] = {(cuuint64_t)mn, (cuuint64_t)kdim};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)BK};
-    cuuint32_t estr[2] = {1, 1};
-    r = g_encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, mn_swizzle(), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     // contiguous along MN: element (x, kk) at base[kk * ld + x]; viewed as {32, K, MN/32} so that one box
     // lands as [MN/32 chunks][BK k-rows][32 floats] — the canonical MN-major SWIZZLE_128B layout
@@ -612,33 +568,11 @@ CUtensorMap make_operand_map(const float* base, bool mn_major, int mn, int kdim,
     cuuint32_t box[3] = {32, (cuuint32_t)BK, (cuuint32_t)(rows / 32)};
     cuuint32_t estr[3] = {1, 1, 1};
     r = g_encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, mn_swizzle(), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, MN_TMA_SWIZZLE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
   return map;
-}
-
-TuneParams tune_params() {
-  static TuneParams tp = [] {
-    TuneParams t;
-    t.k_lbo = 16, t.k_sbo = 1024, t.k_step = UMMA_K * 4;          // 8-row atoms 1024 B apart; +32 B per K step
-    t.mn_lbo = BK * 128, t.mn_sbo = 512, t.mn_step = 1024;        // 32-wide MN chunks 4096 B apart; 4-row atoms; +8 k-rows per step
-    t.mn_layout = 1;
-    auto env = [](const char* name, uint32_t& v) {
-      if (const char* s = getenv(name)) v = (uint32_t)strtoul(s, nullptr, 0);
-    };
-    env("CG_TF32_K_LBO", t.k_lbo), env("CG_TF32_K_SBO", t.k_sbo), env("CG_TF32_K_STEP", t.k_step);
-    env("CG_TF32_MN_LBO", t.mn_lbo), env("CG_TF32_MN_SBO", t.mn_sbo), env("CG_TF32_MN_STEP", t.mn_step);
-    t.mn_chunked = 0;
-    env("CG_TF32_MN_CHUNKED", t.mn_chunked), env("CG_TF32_MN_LAYOUT", t.mn_layout);
-    t.pair_peer_arrives = 0, t.pair_small_only = 0;
-    env("CG_TF32_PAIR_PEER_ARRIVES", t.pair_peer_arrives), env("CG_TF32_PAIR_SMALL_ONLY", t.pair_small_only);
-    t.debug_clock = 0;
-    env("CG_TF32_DEBUG_CLOCK", t.debug_clock);
-    return t;
-  }();
-  return tp;
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -653,7 +587,7 @@ void launch_variant(const CUtensorMap& ma, const CUtensorMap& mb, float* C, int 
   }
   const int tiles = (m / BM) * (n / BN);
   const int grid = tiles < g_max_ctas ? tiles : g_max_ctas;
-  gemm_tf32_kernel<BN, A_MN, B_MN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(ma, mb, C, m, n, k, ldc, epi.mode, epi.lr, tune_params());
+  gemm_tf32_kernel<BN, A_MN, B_MN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(ma, mb, C, m, n, k, ldc, epi.mode, epi.lr);
   CG_CUDA(cudaGetLastError());
 }
 
@@ -663,9 +597,8 @@ void launch_bn(const float* A, bool ta, const float* B, bool tb, float* C, int m
   // op(A)(i, kk): not transposed => A[kk * lda + i] (M-contiguous, MN-major); transposed => A[i * lda + kk] (K-major)
   // op(B)(kk, j): not transposed => B[j * ldb + kk] (K-major);                transposed => B[kk * ldb + j] (MN-major)
   const bool a_mn = !ta, b_mn = tb;
-  const bool chunked = tune_params().mn_chunked != 0;
-  const CUtensorMap ma = make_operand_map(A, a_mn, m, k, lda, BM, chunked);
-  const CUtensorMap mb = make_operand_map(B, b_mn, n, k, ldb, BN, chunked);
+  const CUtensorMap ma = make_operand_map(A, a_mn, m, k, lda, BM);
+  const CUtensorMap mb = make_operand_map(B, b_mn, n, k, ldb, BN);
   if (a_mn && !b_mn) launch_variant<BN, true, false>(ma, mb, C, m, n, k, ldc, epi, stream);
   else if (a_mn && b_mn) launch_variant<BN, true, true>(ma, mb, C, m, n, k, ldc, epi, stream);
   else if (!a_mn && !b_mn) launch_variant<BN, false, false>(ma, mb, C, m, n, k, ldc, epi, stream);
@@ -674,7 +607,7 @@ void launch_bn(const float* A, bool ta, const float* B, bool tb, float* C, int m
 
 template <bool A_MN, bool B_MN>
 void launch_pair_variant(const CUtensorMap& ma, const CUtensorMap& mb_big, const CUtensorMap& mb_small, float* C, int m, int n,
-                         int k, int ldc, const GemmEpilogue& epi, int cols_per_pair, int wmax, int pairs, cudaStream_t stream) {
+                         int k, int ldc, const GemmEpilogue& epi, int wmax, int pairs, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES2 * STAGE_BYTES2 + 256 + 1024;
   static bool configured = false;
   if (!configured) {
@@ -693,17 +626,13 @@ void launch_pair_variant(const CUtensorMap& ma, const CUtensorMap& mb_big, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_pair_kernel<A_MN, B_MN>, ma, mb_big, mb_small, C, m, n, k, ldc, epi.mode, epi.lr,
-                             tune_params(), cols_per_pair, wmax));
+  CG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_pair_kernel<A_MN, B_MN>, ma, mb_big, mb_small, C, m, n, k, ldc, epi.mode, epi.lr, wmax));
 }
 
 // Off by default: measured on B200 (tools/gemm_sweep.py) the pair kernel's main loop is marginally faster per k-block
 // (0.356 vs 0.374 us) but its fixed cost (cluster launch, two cluster barriers) is higher (9.4 vs 4.3 us), so at the
-// hot-path shapes (K = 1024 / 4096) the single-CTA kernel wins or ties. cg_set_tf32_pair(1) / CG_TF32_PAIR=1 selects it.
-int g_pair_enabled = [] {
-  const char* e = getenv("CG_TF32_PAIR");
-  return e ? atoi(e) : 0;
-}();
+// hot-path shapes (K = 1024 / 4096) the single-CTA kernel wins or ties. cg_set_tf32_pair(1) selects it.
+int g_pair_enabled = 0;
 bool pair_kernel_enabled() { return g_pair_enabled != 0; }
 
 bool pair_eligible(int m, int n, int k) { return pair_kernel_enabled() && m % 256 == 0 && n % 64 == 0 && k % BK == 0; }
@@ -715,22 +644,16 @@ void launch_pair(const float* A, bool ta, const float* B, bool tb, float* C, int
   // widest column tile <= 256 that divides n (K-major B halves need 16-row boxes, MN-major 32-column chunks)
   const int gran = b_mn ? 64 : 32;
   int wmax = 256;
-  static const int forced = [] {
-    const char* e = getenv("CG_TF32_PAIR_W");
-    return e ? atoi(e) : 0;
-  }();
-  if (forced > 0) wmax = forced;
   while (wmax > gran && n % wmax != 0) wmax -= gran;
   const int tiles = total / wmax;
   const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
-  const int cols = 0;
-  const CUtensorMap ma = make_operand_map(A, a_mn, m, k, lda, BM, false);
-  const CUtensorMap mb_big = make_operand_map(B, b_mn, n, k, ldb, wmax / 2, false);
-  const CUtensorMap mb_small = make_operand_map(B, b_mn, n, k, ldb, b_mn ? 32 : 16, false);
-  if (a_mn && !b_mn) launch_pair_variant<true, false>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, cols, wmax, pairs, stream);
-  else if (a_mn && b_mn) launch_pair_variant<true, true>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, cols, wmax, pairs, stream);
-  else if (!a_mn && !b_mn) launch_pair_variant<false, false>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, cols, wmax, pairs, stream);
-  else launch_pair_variant<false, true>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, cols, wmax, pairs, stream);
+  const CUtensorMap ma = make_operand_map(A, a_mn, m, k, lda, BM);
+  const CUtensorMap mb_big = make_operand_map(B, b_mn, n, k, ldb, wmax / 2);
+  const CUtensorMap mb_small = make_operand_map(B, b_mn, n, k, ldb, b_mn ? 32 : 16);
+  if (a_mn && !b_mn) launch_pair_variant<true, false>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
+  else if (a_mn && b_mn) launch_pair_variant<true, true>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
+  else if (!a_mn && !b_mn) launch_pair_variant<false, false>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
+  else launch_pair_variant<false, true>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
 }
 
 }  // namespace
@@ -753,8 +676,7 @@ void launch_gemm_tf32(const float* A, bool ta, const float* B, bool tb, float* C
   if (!gemm_tf32_aligned(A, B, lda, ldb))
     throw Error("tcgen05 product: operands must be 128-byte aligned with leading dimensions in multiples of 4");
   if (pair_eligible(m, n, k)) return launch_pair(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
-  static const bool force128 = getenv("CG_TF32_BN128") != nullptr;
-  if (n % 256 == 0 && !force128) launch_bn<256>(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
+  if (n % 256 == 0) launch_bn<256>(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
   else launch_bn<128>(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
 }
 

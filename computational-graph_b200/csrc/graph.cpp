@@ -30,9 +30,18 @@ const std::vector<float>* plan_only_shadow(const float* ptr) {
 DevBuf::~DevBuf() {
   if (placeholder) g_shadows.erase(ptr);
   if (owned && ptr && !placeholder) {
-    dp_forget(ptr, (n ? n : 1) * sizeof(float));  // peers may hold this buffer open (dp.cpp)
-    cudaFree(ptr);
+    if (symm) symm_free(ptr);  // back to the multicast heap's free list (symm.cpp); never unmapped under a peer
+    else if (!dp_retire(ptr, (n ? n : 1) * sizeof(float))) cudaFree(ptr);  // peers may hold this buffer open (dp.cpp)
   }
+}
+BufRef DevBuf::alloc_symm(size_t n) {
+  if (g_plan_only) return alloc(n);
+  auto b = std::make_shared<DevBuf>();
+  b->n = n;
+  b->owned = true;
+  b->symm = true;
+  b->ptr = static_cast<float*>(symm_alloc((n ? n : 1) * sizeof(float)));
+  return b;
 }
 BufRef DevBuf::alloc(size_t n) {
   auto b = std::make_shared<DevBuf>();

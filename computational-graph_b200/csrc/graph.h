@@ -21,6 +21,7 @@ struct DevBuf {
   size_t n = 0;
   std::shared_ptr<void> keepalive;  // arena that owns `ptr`, when not owned here
   bool owned = false;
+  bool symm = false;         // lives in the symmetric multicast heap (symm.cpp): data-parallel weights and gradient slots
   bool placeholder = false;  // plan-only mode: an address that is never dereferenced
   // plan-only mode: the INITIAL contents (storage order) this buffer would have been given — never computed on, only
   // written out next to the generated resident-kernel source (CG_TAPE_JIT_DUMP) for the CPU-side emulator test
@@ -30,6 +31,7 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf();
   static std::shared_ptr<DevBuf> alloc(size_t n);
+  static std::shared_ptr<DevBuf> alloc_symm(size_t n);  // collective over the data-parallel ranks
 };
 using BufRef = std::shared_ptr<DevBuf>;
 
@@ -59,6 +61,8 @@ struct Function {
   std::shared_ptr<Expr> body;
   std::shared_ptr<Plan> plan;  // compiled tape, cached on the root the user optimises
   std::shared_ptr<Plan> eval_plan;  // forward-only tape of `eval` (optimize.rs:8-32)
+  std::shared_ptr<Function> negated;  // `-self`, built by the first `maximize` (optimize.rs:74-81) and reused
+  bool negated_identity = false;      // whether that construction hit the identity elimination (`-0 == 0`)
   int plan_mode = -1;
 };
 

@@ -294,8 +294,9 @@ struct Builder {
         // the result (ops.rs:405), which coincides for its square-only products (Q7)
         to_f1 = equals_dot(shape_of(*e.f1), error, false, read(*e.f2), !e.t2);
         to_f2 = equals_dot(shape_of(*e.f2), read(*e.f1), !e.t1, error, false);
-        if (dp && e.f2->has_params) {
-          // Data parallel: the rows of every left operand are the sharded batch dimension, so the
+        if (dp && p.mode == 1 && e.f2->has_params) {
+          // Data parallel (dag mode only — exact mode and C1-C3 run as replicas, its in-line SGD is
+          // interleaved with the walk): the rows of every left operand are the sharded batch dimension, so the
           // right-operand (weight) gradient X^T.E is a per-rank partial sum: sum-allreduce it, in place.
           Instr ar;
           ar.op = IOp::AllReduce;
@@ -827,9 +828,16 @@ void assign_memory(Plan& p) {
     else if (s.kind == Step::DPUPDATE) reduced[root_of(s.ins.a)] = 1;
   const int hold = 64;  // steps (a backward LSTM step is ~25 kernels: about 20 gradient buffers in rotation)
   constexpr size_t ALIGN = 256;
-  std::map<size_t, std::vector<size_t>> free_slots;  // bytes -> offsets
+  // In-switch exchange (dp_multimem_update_kernel): the partial gradients it sums must sit in the symmetric multicast
+  // heap, at the same offset on every rank — they get an arena of their own there (index 1).
+  const bool mc = dp_multimem_active();
+  std::vector<char> in_mc(p.vals.size(), 0);
+  if (mc)
+    for (const Step& s : p.steps)
+      if (s.kind == Step::DPUPDATE) in_mc[root_of(s.ins.a)] = 1;
+  std::map<size_t, std::vector<size_t>> free_slots_of[2];  // bytes -> offsets
   std::vector<std::vector<int>> release_at(p.steps.size());
-  size_t top = 0;
+  size_t top_of[2] = {0, 0};
   std::vector<size_t> off(p.vals.size(), SIZE_MAX);
   for (size_t si = 0; si < p.steps.size(); si++) {
     step_defs_uses(p.steps[si], defs, uses);
@@ -837,7 +845,8 @@ void assign_memory(Plan& p) {
       Val& val = p.vals[v];
       if (val.fixed || val.alias_of >= 0) continue;
       size_t bytes = (val.sh.n() * sizeof(float) + ALIGN - 1) / ALIGN * ALIGN;
-      auto& fl = free_slots[bytes];
+      auto& fl = free_slots_of[(int)in_mc[v]][bytes];
+      size_t& top = top_of[(int)in_mc[v]];
       if (!fl.empty()) {
         off[v] = fl.back();
         fl.pop_back();
@@ -851,15 +860,16 @@ void assign_memory(Plan& p) {
     }
     for (int v : release_at[si]) {
       size_t bytes = (p.vals[v].sh.n() * sizeof(float) + ALIGN - 1) / ALIGN * ALIGN;
-      free_slots[bytes].push_back(off[v]);
+      free_slots_of[(int)in_mc[v]][bytes].push_back(off[v]);
     }
   }
-  p.stats.arena_bytes = top;
-  if (top) p.arena = DevBuf::alloc(top / sizeof(float));
+  p.stats.arena_bytes = top_of[0] + top_of[1];
+  if (top_of[0]) p.arena = DevBuf::alloc(top_of[0] / sizeof(float));
+  if (top_of[1]) p.dp_arena = DevBuf::alloc_symm(top_of[1] / sizeof(float));
   for (size_t v = 0; v < p.vals.size(); v++) {
     Val& val = p.vals[v];
     if (val.fixed) val.ptr = val.fixed;
-    else if (off[v] != SIZE_MAX) val.ptr = p.arena->ptr + off[v] / sizeof(float);
+    else if (off[v] != SIZE_MAX) val.ptr = (in_mc[v] ? p.dp_arena->ptr : p.arena->ptr) + off[v] / sizeof(float);
   }
   for (size_t v = 0; v < p.vals.size(); v++) {
     Val& val = p.vals[v];
@@ -912,7 +922,53 @@ void finalize_steps(Plan& p) {
 
 // Data parallel: every buffer a fused exchange touches (the partial gradient in the arena, the weight leaf) is opened
 // by every peer, and the peer pointers go into the step. Collective: every rank builds the same plan at the same time.
+// In-switch form: the gradient slot and the weight must be heap memory at the same (segment, offset) on every rank —
+// checked here, collectively, so that every rank takes the same decision.
+void bind_dp_multimem(Plan& p) {
+  std::vector<unsigned long long> where;
+  bool local_ok = true;
+  for (const Step& s : p.steps) {
+    if (s.kind != Step::DPUPDATE) continue;
+    for (const float* ptr : {p.vals[s.ins.a].ptr, p.vals[s.ins.dst].ptr}) {
+      unsigned long long seg = ~0ull, off = ~0ull;
+      if (!symm_locate(ptr, &seg, &off, nullptr)) local_ok = false;
+      where.push_back(seg);
+      where.push_back(off);
+    }
+  }
+  if (where.empty()) return;
+  where.push_back(local_ok ? 1 : 0);
+  std::vector<unsigned char> all = dp_allgather_bytes(where.data(), where.size() * sizeof(unsigned long long));
+  const size_t stride = where.size() * sizeof(unsigned long long);
+  for (size_t r = 0; r * stride < all.size(); r++)
+    if (memcmp(all.data() + r * stride, where.data(), stride) != 0 || !local_ok)
+      throw Error("data parallel: the ranks' weights and gradient slots are not at the same offsets of the multicast heap "
+                  "(ranks must build the same graphs in the same order); cg_dp_set_multimem(0) selects the peer-memory exchange");
+  for (Step& s : p.steps) {
+    if (s.kind != Step::DPUPDATE) continue;
+    if (p.vals[s.ins.c_in].ptr != p.vals[s.ins.dst].ptr) throw Error("internal: fused data-parallel update is not in place");
+    void *g_mc = nullptr, *w_mc = nullptr;
+    symm_locate(p.vals[s.ins.a].ptr, nullptr, nullptr, &g_mc);
+    symm_locate(p.vals[s.ins.dst].ptr, nullptr, nullptr, &w_mc);
+    memset(&s.mc, 0, sizeof s.mc);
+    s.mc.g_mc = static_cast<const float*>(g_mc);
+    s.mc.w_uc = p.vals[s.ins.dst].ptr;
+    s.mc.w_mc = static_cast<float*>(w_mc);
+    s.mc.lr = s.ins.imm;
+    s.mc.n = p.vals[s.ins.dst].sh.n();
+    dp_fill_mc_flags(s.mc);
+    s.use_mc = true;
+    p.stats.dp_multimem_updates++;
+  }
+}
+
 void bind_dp_updates(Plan& p) {
+  if (dp_multimem_active()) {
+    if (!plan_only()) return bind_dp_multimem(p);
+    for (Step& s : p.steps)
+      if (s.kind == Step::DPUPDATE) s.use_mc = true, p.stats.dp_multimem_updates++;
+    return;
+  }
   std::vector<const void*> ptrs;
   for (const Step& s : p.steps)
     if (s.kind == Step::DPUPDATE) {
@@ -939,6 +995,33 @@ void bind_dp_updates(Plan& p) {
   }
 }
 
+// In-switch exchange: every weight it will update (a matrix parameter that is the right operand of a product — the
+// pattern fuse_dp_update recognises) moves into the symmetric multicast heap before the tape takes its address. The
+// walk is memoised per shared body and visits the leaves in the deterministic order every rank shares, so the heap
+// hands out the same offsets everywhere. Returns whether anything moved.
+bool migrate_dp_weights(Function& root) {
+  bool moved = false;
+  std::unordered_set<const Expr*> seen;
+  std::function<void(Function&)> walk = [&](Function& f) {
+    Expr& e = *f.body;
+    if (is_leaf(e.kind) || !seen.insert(&e).second) return;
+    if (e.f1) walk(*e.f1);
+    if (e.f2) walk(*e.f2);
+    if (e.kind != Kind::Dot || !e.f2 || e.f2->body->kind != Kind::Param) return;
+    Value& v = e.f2->value;
+    if (!v.is_matrix || !v.buf || v.buf->symm || v.size() % 4 || v.size() < dp_fused_min_elems()) return;
+    if (plan_only()) return;
+    BufRef nb = DevBuf::alloc_symm(v.size());
+    Runtime& rt = Runtime::get();
+    CG_CUDA(cudaMemcpyAsync(nb->ptr, v.buf->ptr, v.size() * sizeof(float), cudaMemcpyDeviceToDevice, rt.stream));
+    CG_CUDA(cudaStreamSynchronize(rt.stream));  // the old buffer may be freed by the assignment below
+    v.buf = nb;
+    moved = true;
+  };
+  walk(root);
+  return moved;
+}
+
 }  // namespace
 
 void build_vm(Plan& p);
@@ -957,6 +1040,7 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root, bool 
   p.ew_jit_min = rt.ew_jit_min;
   p.hoist = rt.hoist;
 
+  if (p.mode == 1 && !forward_only && dp_multimem_active() && migrate_dp_weights(root)) root.eval_plan.reset();
   Builder b(p, lr, rt.fix_act_grad);
   b.forward(root);
   const Shape rsh = Builder::shape_of(root);
@@ -1097,7 +1181,7 @@ std::string plan_describe(const Plan& p) {
                  (int)s.ins.tb, s.ins.epi);
       } break;
       case Step::ALLREDUCE: snprintf(line, sizeof line, "%zu ALLREDUCE n=%zu\n", i, p.vals[s.ins.dst].sh.n()); break;
-      case Step::DPUPDATE: snprintf(line, sizeof line, "%zu DPUPDATE n=%zu\n", i, p.vals[s.ins.dst].sh.n()); break;
+      case Step::DPUPDATE: snprintf(line, sizeof line, "%zu DPUPDATE n=%zu%s\n", i, p.vals[s.ins.dst].sh.n(), s.use_mc ? " multimem" : ""); break;
     }
     out += line;
   }
@@ -1139,7 +1223,10 @@ void plan_launch_step(Plan& p, size_t index, cudaStream_t stream) {
                     p.tf32 != 0, stream);
       } break;
       case Step::ALLREDUCE: dp_allreduce_sum(p.vals[s.ins.dst].ptr, p.vals[s.ins.dst].sh.n(), stream); break;
-      case Step::DPUPDATE: launch_dp_reduce_update(s.dp, stream); break;
+      case Step::DPUPDATE:
+        if (s.use_mc) launch_dp_multimem_update(s.mc, stream);
+        else launch_dp_reduce_update(s.dp, stream);
+        break;
     }
   }
 }

@@ -69,6 +69,8 @@ struct Step {
   EwGroup ew;
   Instr ins;  // AVG / GEMM / ALLREDUCE
   DpReduceArgs dp;  // DPUPDATE, filled after memory assignment (peer pointers)
+  DpMcArgs mc;      // DPUPDATE through the NVSwitch (use_mc): multicast addresses in the symmetric heap
+  bool use_mc = false;
   EwProgram prog;  // EW, filled after memory assignment
   const EwKernel* jit = nullptr;  // EW: the program specialised into straight-line code (large domains only)
 };
@@ -101,6 +103,7 @@ void launch_tape_jit(const TapeKernel* k, int iters, float* trace, cudaStream_t 
 struct PlanStats {
   size_t tape_instrs = 0, live_instrs = 0, ew_groups = 0, gemms = 0, gemms_fused_sgd = 0, reduces = 0;
   size_t arena_bytes = 0, kernels_per_iter = 0, ew_specialised = 0, allreduces = 0, dp_fused_updates = 0, vm_resident = 0, tape_smem_bytes = 0, quiet_variant = 0;
+  size_t dp_multimem_updates = 0;  // of dp_fused_updates: done inside the NVSwitch (multimem)
   double gemm_flop_per_iter = 0.0, ew_bytes_per_iter = 0.0, quiet_ew_bytes_per_iter = 0.0;
 };
 
@@ -129,6 +132,7 @@ struct Plan {
   std::vector<Instr> tape;
   std::vector<Step> steps;
   BufRef arena;
+  BufRef dp_arena;   // gradient slots of the in-switch exchange: symmetric multicast heap (symm.cpp)
   BufRef eval_root;  // forward-only plans (`eval`): the root value, in a buffer of the plan's own
   PlanStats stats;
   float lr = 0.0f;

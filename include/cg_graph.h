@@ -135,6 +135,7 @@ typedef struct {
   unsigned long long tape_smem_bytes;  /* compiled resident kernel: shared memory holding every value of the plan */
   unsigned long long quiet_variant;    /* 1: iterations with an unobservable root value skip its store (cg_set_elide_root) */
   double quiet_ew_bytes_per_iter;      /* elementwise bytes of such an iteration */
+  unsigned long long dp_multimem_updates; /* of dp_fused_updates: summed and broadcast inside the NVSwitch (multimem) */
 } cg_plan_stats;
 int cg_plan_stats_get(cg_function *f, float learn_rate, cg_plan_stats *out); /* compiles the plan if needed */
 /* One text line per kernel of the compiled iteration, in launch order ("<i> GEMM m= n= k= ta= tb= epi=", "<i> EW n= in= out=
@@ -161,10 +162,20 @@ int cg_dp_init(int rank, int world, const unsigned char id[CG_DP_ID_BYTES]); /* 
 int cg_dp_shutdown(void);
 /* Plan-only mode: pretend to be one of `world` ranks (fused: with the peer-memory exchange available) so that the
  * data-parallel tape can be inspected on a machine without GPUs. */
-int cg_dp_plan_only(int world, int fused);
+int cg_dp_plan_only(int world, int fused); /* fused: 0 ncclAllReduce, 1 peer-memory exchange, 2 in-switch exchange */
 /* 1 when the fused all-reduce + update kernel over NVLink peer memory (CUDA IPC) is in use for weights of at least
  * CG_DP_FUSED_MIN elements (default 2^18); 0 when the ranks fell back to ncclAllReduce (or CG_DP_FUSED=0). */
 int cg_dp_fused(void);
+/* In-switch exchange (NVLS): the weights and gradient slots of a data-parallel plan live in a symmetric multicast heap
+ * (VMM memory bound to a CUDA multicast object on every rank) and the fused kernel sums with multimem.ld_reduce and
+ * broadcasts with multimem.st — (1 + 1/world) n bytes per GPU and direction instead of 2 (world-1)/world n.
+ * cg_dp_multimem_supported: the heap could be created at cg_dp_init (else cg_dp_multimem_reason says why not);
+ * cg_dp_multimem: plans built now use it. cg_dp_set_multimem: 0 never, 1 (default) from three ranks up — below that the
+ * peer-memory kernel moves fewer bytes — 2 always. Also CG_DP_MULTIMEM=0 (environment, read at cg_dp_init). */
+int cg_dp_multimem_supported(void);
+int cg_dp_multimem(void);
+const char *cg_dp_multimem_reason(void);
+int cg_dp_set_multimem(int mode);
 int cg_set_device(int device);
 
 #ifdef __cplusplus

@@ -26,16 +26,19 @@ def main():
     ap.add_argument("--inp", type=int, default=40)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl", "multimem"],
                     help="fused: the all-reduce + SGD update kernel over NVLink peer memory (dp_kernels.cu) for every "
-                         "weight; nccl: ncclAllReduce followed by the elementwise update")
+                         "weight; multimem: the same exchange summed and broadcast inside the NVSwitch (multicast heap, "
+                         "symm.cpp); nccl: ncclAllReduce followed by the elementwise update")
     a = ap.parse_args()
     # read once by the library (dp.cpp), so set before it loads
-    if a.exchange == "fused":
+    if a.exchange in ("fused", "multimem"):
         os.environ["CG_DP_FUSED"] = "1"
         os.environ["CG_DP_FUSED_MIN"] = "0"
     else:
         os.environ["CG_DP_FUSED"] = "0"
+    if a.exchange != "multimem":
+        os.environ["CG_DP_MULTIMEM"] = "0"
     import torch
     import torch.distributed as dist
     import computational_graph_b200 as pkg
@@ -56,6 +59,15 @@ def main():
     api.set_device(local)
     pkg.dp.init_from_torch_distributed(api, local)
     note("library communicator up")
+    if a.exchange == "multimem":
+        if not api.dp_multimem_supported():
+            note(f"multicast heap unavailable: {api.dp_multimem_reason()}")
+            if rank == 0:
+                print(f"dp_check world={world} exchange=multimem -> UNAVAILABLE ({api.dp_multimem_reason()})")
+            dist.destroy_process_group()
+            sys.exit(3)
+        api.dp_set_multimem(2)  # also at 2 ranks, where the default keeps the peer-memory kernel
+        assert api.dp_multimem()
     api.set_mode("dag")
     api.set_tf32(bool(a.tf32))
 
@@ -68,8 +80,10 @@ def main():
     st = api.plan_stats(f, 0.01)
     note(f"plan built: {st['kernels_per_iter']} kernels/iter, {st['dp_fused_updates']} fused exchanges, "
          f"{st['allreduces']} ncclAllReduce")
-    if a.exchange == "fused":
-        assert api.dp_fused() and st["dp_fused_updates"] > 0 and st["allreduces"] == 0, "fused exchange not in use"
+    if a.exchange == "multimem":
+        assert st["dp_multimem_updates"] == st["dp_fused_updates"] > 0 and st["allreduces"] == 0, "in-switch exchange not in use"
+    elif a.exchange == "fused":
+        assert api.dp_fused() and st["dp_fused_updates"] > 0 and st["dp_multimem_updates"] == 0 and st["allreduces"] == 0, "fused exchange not in use"
     else:
         assert not api.dp_fused() and st["dp_fused_updates"] == 0 and st["allreduces"] > 0, "NCCL exchange not in use"
     tr1 = np.array(f.minimize({}, 0.01, 1, trace=True))

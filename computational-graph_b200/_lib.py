@@ -68,6 +68,7 @@ class ProductApi(Api):
         lib.cg_dp_shutdown.restype = C.c_int
         lib.cg_dp_fused.restype = C.c_int
         lib.cg_dp_multimem.restype = C.c_int
+        lib.cg_dp_set_fused_min.restype, lib.cg_dp_set_fused_min.argtypes = C.c_int, [C.c_longlong]
         lib.cg_dp_multimem_supported.restype = C.c_int
         lib.cg_dp_multimem_reason.restype = C.c_char_p
         lib.cg_dp_set_multimem.restype, lib.cg_dp_set_multimem.argtypes = C.c_int, [C.c_int]
@@ -198,6 +199,10 @@ class ProductApi(Api):
     def dp_fused(self) -> bool:
         """True when weight gradients are exchanged by the fused peer-memory kernel rather than ncclAllReduce."""
         return bool(self.lib.cg_dp_fused())
+
+    def dp_set_fused_min(self, min_elems: int):
+        """Weights with fewer elements stay on ncclAllReduce + update (default 2^18; < 0 restores it)."""
+        self._check(self.lib.cg_dp_set_fused_min(int(min_elems)))
 
     def dp_multimem(self) -> bool:
         """True when plans built now exchange weight gradients inside the NVSwitch (multimem.ld_reduce / multimem.st)."""

@@ -337,6 +337,24 @@ class Function:
     def all_equal(self, x: float) -> bool:
         return bool(self._api._sym("all_equal")(self._h, float(x)))
 
+    def set_leaf(self, i: int, value) -> None:
+        """Checkpoint restore (the reference can only `Display` its parameters, src/print.rs:71-80):
+        overwrite leaf `i` of `leaves()` with `value` — a [rows, cols] array (or a scalar) as `leaves()` returns it."""
+        arr = np.ascontiguousarray(np.atleast_1d(np.asarray(value, dtype=np.float32)))
+        fn = self._api._sym("leaf_set")
+        fn.restype, fn.argtypes = C.c_int, [_F, C.c_int, _FP]
+        if fn(self._h, int(i), _fptr(arr)) != 0:
+            msg = self._api._last_error().decode() if self._api._last_error is not None else "leaf_set failed"
+            raise GraphError(msg or f"no leaf {i}")
+
+    def load_leaves(self, saved) -> None:
+        """Restore every leaf from a list as returned by `leaves()` (names must match, in order)."""
+        cur = self.leaves()
+        if [n for n, _ in cur] != [n for n, _ in saved]:
+            raise GraphError("checkpoint does not match this function's parameter leaves")
+        for i, (_, v) in enumerate(saved):
+            self.set_leaf(i, v)
+
     def leaves(self) -> List[Tuple[str, Union[np.float32, np.ndarray]]]:
         """Every parameter leaf of the tree in memoised post-order. Each *use site* of a param is its
         own leaf (the reference clones the value into every use, Q1 / src/function.rs:10-16)."""

@@ -189,7 +189,9 @@ bool dp_multimem_active() {
   return g_multimem_mode == 2 || g_nccl.world >= 3;
 }
 
+static long long g_fused_min = -1;  // < 0: CG_DP_FUSED_MIN from the environment, else 2^18
 size_t dp_fused_min_elems() {
+  if (g_fused_min >= 0) return (size_t)g_fused_min;
   static const size_t v = [] {
     const char* e = getenv("CG_DP_FUSED_MIN");
     return e ? (size_t)atoll(e) : (size_t)1 << 18;  // 1 MiB: below that the exchange is latency, not bandwidth
@@ -540,6 +542,15 @@ int cg_dp_init(int rank, int world, const unsigned char id[CG_DP_ID_BYTES]) {
   }
 }
 int cg_dp_fused(void) { return dp_fused_available() ? 1 : 0; }
+int cg_dp_set_fused_min(long long min_elems) {
+  try {
+    if (g_fused_min != min_elems) Runtime::get().dp_epoch++;
+    g_fused_min = min_elems;
+    return 0;
+  } catch (const std::exception& e) {
+    return cg_dp_set_error(e.what());
+  }
+}
 int cg_dp_multimem(void) { return dp_multimem_active() ? 1 : 0; }
 int cg_dp_multimem_supported(void) { return symm_available() ? 1 : 0; }
 const char* cg_dp_multimem_reason(void) { return symm_unavailable_reason(); }

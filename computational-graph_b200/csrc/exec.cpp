@@ -22,10 +22,7 @@ static void upload_inputs(Plan& p, const std::vector<Arg>& args) {
   }
 }
 
-static void print_value(const Value& v) {
-  // optimize.rs:66-68 `self.value().print()`; the reference's Display formatting (print.rs) is out of scope
-  std::vector<float> host(v.size());
-  value_download(v, host.data());
+static void print_host_value(const Value& v, const float* host) {
   if (!v.is_matrix) {
     printf("%g\n", host[0]);
     return;
@@ -35,6 +32,48 @@ static void print_value(const Value& v) {
     printf("\n");
   }
 }
+static void print_value(const Value& v) {
+  // optimize.rs:66-68 `self.value().print()`; the reference's Display formatting (print.rs) is out of scope
+  std::vector<float> host(v.size());
+  value_download(v, host.data());
+  print_host_value(v, host.data());
+}
+
+// The `print_freq` loss log (optimize.rs:66-68; SURVEY §5 "per-iteration loss ring buffer on device, D2H every print_freq
+// only" / §8f-3). The reference prints inside the loop, which on a GPU means a blocking read-back per print; here the
+// printed root values are copied device-to-device into a small ring as the iterations are enqueued, and the ring is
+// read back (one copy, one synchronisation) and printed when it is full and at the end of the call — same lines, same
+// order, no synchronisation inside the loop.
+struct LossRing {
+  static constexpr size_t kSlots = 32, kMaxBytes = (size_t)64 << 20;
+  const Value& v;
+  size_t n, slots = 0, used = 0;
+  float* dev = nullptr;
+  std::vector<float> host;
+  cudaStream_t stream;
+  LossRing(const Value& value, size_t root_n, size_t prints, cudaStream_t st) : v(value), n(root_n), stream(st) {
+    slots = std::min(prints, kSlots);
+    while (slots > 1 && slots * n * sizeof(float) > kMaxBytes) slots /= 2;
+    if (slots && slots * n * sizeof(float) <= kMaxBytes) CG_CUDA(cudaMalloc(&dev, slots * n * sizeof(float)));
+    host.resize(dev ? slots * n : 0);
+  }
+  bool active() const { return dev != nullptr; }
+  void push(const float* root_ptr) {  // enqueued right behind the iteration whose value is printed
+    CG_CUDA(cudaMemcpyAsync(dev + used * n, root_ptr, n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    if (++used == slots) flush();
+  }
+  void flush() {
+    if (!used) return;
+    CG_CUDA(cudaMemcpyAsync(host.data(), dev, used * n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CG_CUDA(cudaStreamSynchronize(stream));
+    for (size_t k = 0; k < used; k++) print_host_value(v, host.data() + k * n);
+    fflush(stdout);
+    used = 0;
+  }
+  ~LossRing() {
+    if (dev) cudaFree(dev);
+  }
+};
 
 // ---------------------------------------------------------------------------------------------------------
 // CUDA-graph capture of one iteration as a DAG: steps are spread over several streams and joined with events,
@@ -444,6 +483,12 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
   ensure_graph(p, rt);
   if (p.quiet) ensure_graph(*p.quiet, rt);
 
+  const size_t prints = print_freq > 0 ? (size_t)(iters / print_freq) : 0;
+  LossRing ring(f.value, p.root_n, prints, rt.stream);
+  auto print_now = [&] {
+    if (ring.active()) ring.push(p.root_ptr);
+    else print_value(f.value);
+  };
   float* trace_dev = nullptr;
   const bool direct_trace = trace && iters == 1;  // one iteration: read the root value straight back
   if (trace && iters > 1) CG_CUDA(cudaMalloc(&trace_dev, (size_t)iters * p.root_n * sizeof(float)));
@@ -452,7 +497,7 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
   for (int i = 0; i < iters; i++) {
     if (i == 0 && io) {
       launch_io_graph(p, rt, args, trace);
-      if (print_freq > 0 && (i + 1) % print_freq == 0) print_value(f.value);
+      if (print_freq > 0 && (i + 1) % print_freq == 0) print_now();
       continue;
     }
     // the traced value is the forward value of iteration i, i.e. before its update (Q12)
@@ -469,8 +514,9 @@ void minimize(Function& f, const std::vector<Arg>& args, float lr, int iters, in
     if (trace_dev && !p.root_is_leaf)
       CG_CUDA(cudaMemcpyAsync(trace_dev + (size_t)i * p.root_n, p.root_ptr, p.root_n * sizeof(float),
                               cudaMemcpyDeviceToDevice, rt.stream));
-    if (print_freq > 0 && (i + 1) % print_freq == 0) print_value(f.value);
+    if (print_freq > 0 && (i + 1) % print_freq == 0) print_now();
   }
+  ring.flush();
   if (direct_trace) {
     if (!p.root_is_leaf && !io)
       CG_CUDA(cudaMemcpyAsync(trace, p.root_ptr, p.root_n * sizeof(float), cudaMemcpyDeviceToHost, rt.stream));

@@ -166,6 +166,7 @@ int cg_dp_plan_only(int world, int fused); /* fused: 0 ncclAllReduce, 1 peer-mem
 /* 1 when the fused all-reduce + update kernel over NVLink peer memory (CUDA IPC) is in use for weights of at least
  * CG_DP_FUSED_MIN elements (default 2^18); 0 when the ranks fell back to ncclAllReduce (or CG_DP_FUSED=0). */
 int cg_dp_fused(void);
+int cg_dp_set_fused_min(long long min_elems); /* weights below this stay on ncclAllReduce; < 0: the default (2^18) */
 /* In-switch exchange (NVLS): the weights and gradient slots of a data-parallel plan live in a symmetric multicast heap
  * (VMM memory bound to a CUDA multicast object on every rank) and the fused kernel sums with multimem.ld_reduce and
  * broadcasts with multimem.st — (1 + 1/world) n bytes per GPU and direction instead of 2 (world-1)/world n.

@@ -20,6 +20,21 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b))) / denom
 
 
+def close_err(a, b, tol):
+    """Per-element closeness: max over elements of |a - b| / (tol * |b| + tol * rms(b)); <= 1 passes.
+    Unlike `rel_err` (max-norm relative), a wrong SMALL entry in an array with one large entry does not pass: every
+    element is held to `tol` relative to its own magnitude plus `tol` of the array's typical magnitude."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        raise AssertionError(f"shape mismatch {a.shape} vs {b.shape}")
+    if a.size == 0:
+        return 0.0
+    rms = float(np.sqrt(np.mean(b * b)))
+    bound = tol * np.abs(b) + tol * max(rms, 1e-30)
+    return float(np.max(np.abs(a - b) / bound))
+
+
 def readme_lstm(api, d, T=2, seed=None, batch=None, d_in=None, scale=None):
     """src/main.rs:177-191 (`run_lstm`): T random d x d inputs and a target ~U(-.1,.1), 15 params ~U(-1,1),
     loss (lstm(inputs) - target).sq(). Seeded (seed 300+d)."""

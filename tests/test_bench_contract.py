@@ -10,18 +10,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--no-same-config"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "LSTM fwd+backprop+SGD iterations/sec"
     assert d["unit"] == "iterations/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
-    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1e-6 * 1000.0
-    assert d["config"]["workload"].startswith("BASELINE config 4")
+    assert d["steps"] == 1 and d["warmup"] == 0  # the arm honours the driver's K and W
+    assert d["config"]["workload"].startswith("BASELINE config 5") and d["scaling"] == "strong"
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == d["value"] and cb["sample"]
+    # ms_per_step is what one step of THIS arm took on the clock (a pass over the bounded sample); value scales it to the
+    # whole workload by the sample's flop fraction, and the line says so
+    assert abs(d["ms_per_step"] - 1e3 * cb["sample_seconds_per_pass"]) < 1e-6
+    assert abs(d["value"] - cb["sample_flop_fraction"] / cb["sample_seconds_per_pass"]) <= 1e-9 * d["value"]
+    assert "EXTRAPOLATED" in cb["sample"] and d["step_definition"]
     assert d["e2e"] == {"value": d["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

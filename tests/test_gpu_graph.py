@@ -514,3 +514,54 @@ def test_specialised_elementwise_kernels_lstm_dag(cg, oracle):
         assert np.array_equal(out[0][1][k].view(np.int32), out[1][1][k].view(np.int32)), k
         assert rel_err(out[0][1][k], lo[k]) < 1e-5, k
     assert rel_err(out[0][0], to) < 1e-5
+
+
+@pytest.mark.parametrize("executor", ["resident", "graph"])
+def test_leaf_checkpoint_restore_replays_bit_identically(cg, executor):
+    """save every leaf (`leaves()`), keep training, perturb, restore (`load_leaves` -> cg_leaf_set), and the
+    trajectory from the restored state is bit-identical to the one first taken from it — on both executors."""
+    cg.set_mode("exact")
+    if executor == "graph":
+        cg.set_vm_max_dim(0)
+    f = readme_lstm(cg, 10)
+    f.minimize({}, 0.01, 5)
+    saved = f.leaves()
+    first = np.asarray(f.minimize({}, 0.01, 5, trace=True))
+    for i, (_, v) in enumerate(saved):
+        f.set_leaf(i, np.full_like(v, 0.123))
+    assert all(np.all(v == np.float32(0.123)) for _, v in f.leaves())
+    f.load_leaves(saved)
+    for (n0, v0), (n1, v1) in zip(saved, f.leaves()):
+        assert n0 == n1 and np.array_equal(np.asarray(v0).view(np.int32), np.asarray(v1).view(np.int32))
+    again = np.asarray(f.minimize({}, 0.01, 5, trace=True))
+    assert np.array_equal(first.view(np.int32), again.view(np.int32))
+    x = cg.Function.scalar_param("x", 1.0)
+    g = (x + cg.Function.scalar(3.0)).sq()
+    g.minimize({}, 0.01, 3)
+    g.set_leaf(0, 1.0)
+    assert g.leaves()[0][1] == np.float32(1.0)
+    with pytest.raises(Exception):
+        g.set_leaf(5, 1.0)
+
+
+@pytest.mark.parametrize("executor", ["resident", "graph"])
+def test_print_freq_loss_log(cg, capfd, executor):
+    """`minimize(&args, lr, iters, print_freq)` prints the root value every print_freq iterations (src/optimize.rs:66-68):
+    the lines are the traced values of those iterations, in order — read back from the device-side ring, not with a
+    blocking copy per print."""
+    if executor == "graph":
+        cg.set_vm_max_dim(0)
+
+    def build():
+        F = cg.Function
+        m = F.param("m", cg.Constant(np.array([[0.5, -1.0], [2.0, 0.25]], dtype=np.float32)))
+        return (m * m + F.scalar(1.0)).sq()
+
+    tr = np.asarray(build().minimize({}, 0.01, 7, trace=True))
+    capfd.readouterr()
+    build().minimize({}, 0.01, 7, print_freq=2)
+    out = capfd.readouterr().out.strip().splitlines()
+    assert len(out) == 3 * 2  # three prints of a 2 x 2 matrix, one row per line
+    for k, it in enumerate((1, 3, 5)):
+        rows = np.array([[float(x) for x in out[2 * k + r].split()] for r in range(2)], dtype=np.float32)
+        assert np.allclose(rows, tr[it], rtol=1e-5), (it, rows, tr[it])

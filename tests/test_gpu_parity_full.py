@@ -1,0 +1,121 @@
+"""Round-2 parity cases (VERDICT r1 "close the parity holes"): sizes and iteration counts SURVEY §8(d) specifies, TF32
+error growth over T = 8 against the oracle, and the headline configuration at FULL size against an independent float64
+restatement. Every comparison is per element: |a - b| <= tol * |b| + tol * rms(b) (helpers.close_err) — 1e-5 on the f32
+path, 1e-3 where TF32 products are enabled (north_star), bit-exactness where no transcendental is involved.
+
+Gradients are compared as updates (p_before - p_after) / lr; recovering a gradient from two f32 parameter values
+carries +-ulp(p)/lr of rounding noise, which is added to the bound and nothing else is.
+"""
+import numpy as np
+import pytest
+
+from helpers import c2_graph, close_err, leaves_dict, readme_lstm
+
+pytestmark = pytest.mark.gpu
+
+LR = 0.01
+
+
+def update_err(before, after_got, after_want, tol, lr=LR):
+    """close_err on the recovered gradients, with the f32 recovery noise in the bound."""
+    before = np.asarray(before, dtype=np.float64)
+    gg = (before - np.asarray(after_got, dtype=np.float64)) / lr
+    gw = (before - np.asarray(after_want, dtype=np.float64)) / lr
+    noise = 4 * np.finfo(np.float32).eps * np.maximum(np.abs(before), 1e-30) / lr
+    rms = float(np.sqrt(np.mean(gw * gw)))
+    bound = tol * np.abs(gw) + tol * max(rms, 1e-30) + noise
+    return float(np.max(np.abs(gg - gw) / bound))
+
+
+@pytest.mark.parametrize("d", [5, 10, 15, 20, 25, 30])
+def test_c3_readme_lstm_every_d_100_iterations(cg, oracle, d):
+    """BASELINE config 3 as SURVEY §8(d) specifies it: all six d, 100 iterations, exact mode, the loss trajectory (all d^2
+    elements of the root value per iteration) and every one of the 28 leaves, against the reference-compiled CPU path."""
+    fg, fo = readme_lstm(cg, d), readme_lstm(oracle, d)
+    tg = fg.minimize({}, LR, 100, trace=True)
+    to = fo.minimize({}, LR, 100, trace=True)
+    assert np.all(np.isfinite(to))
+    assert close_err(tg, to, 1e-5) <= 1.0
+    lg, lo = leaves_dict(fg), leaves_dict(fo)
+    assert list(lg) == list(lo) and len(lg) == 28
+    for k in lg:
+        assert close_err(lg[k], lo[k], 1e-5) <= 1.0, k
+
+
+def test_c2_1024_squared_100_steps(cg, oracle):
+    """BASELINE config 2's parity size: 1024 x 1024, 100 SGD steps, trajectory and the three live leaves."""
+    fg, fo = c2_graph(cg, 1024), c2_graph(oracle, 1024)
+    tg = fg.minimize({}, LR, 100, trace=True)
+    to = fo.minimize({}, LR, 100, trace=True)
+    assert close_err(tg, to, 1e-5) <= 1.0
+    lg, lo = leaves_dict(fg), leaves_dict(fo)
+    assert list(lg) == list(lo) and len(lg) == 3
+    for k in lg:
+        assert close_err(lg[k], lo[k], 1e-5) <= 1.0, k
+
+
+_T8 = {}
+
+
+def _t8_oracle(oracle):
+    """The oracle's two iterations of the T = 8 case (47 GFLOP on one core: computed once for both product variants)."""
+    if not _T8:
+        oracle.set_mode("dag")
+        try:
+            fo = readme_lstm(oracle, 512, T=8, seed=808, batch=256, d_in=512, scale=1.0 / np.sqrt(512))
+            before = leaves_dict(fo)
+            t1 = np.asarray(fo.minimize({}, LR, 1, trace=True))
+            after1 = leaves_dict(fo)
+            t2 = np.asarray(fo.minimize({}, LR, 1, trace=True))
+            _T8.update(before=before, after1=after1, after2=leaves_dict(fo), trace=np.concatenate([t1, t2]))
+        finally:
+            oracle.set_mode("exact")
+    return _T8
+
+
+@pytest.mark.parametrize("product,tol", [("f32", 1e-5), ("tf32", 1e-3)])
+def test_lstm_T8_error_growth_against_the_oracle(cg, oracle, product, tol):
+    """LSTM T = 8, B = 256, H = I = 512, dag mode: eight chained time steps of tensor-core products against the f32 CPU
+    oracle — loss trajectory of two iterations, the first iteration's per-leaf gradients and the leaves after the second."""
+    want = _t8_oracle(oracle)
+    cg.set_mode("dag")
+    cg.set_tf32(product == "tf32")
+    fg = readme_lstm(cg, 512, T=8, seed=808, batch=256, d_in=512, scale=1.0 / np.sqrt(512))
+    st = cg.plan_stats(fg, LR)
+    assert st["gemms"] > 0 and st["vm_resident"] == 0
+    t1 = np.asarray(fg.minimize({}, LR, 1, trace=True))
+    after1 = leaves_dict(fg)
+    t2 = np.asarray(fg.minimize({}, LR, 1, trace=True))
+    after2 = leaves_dict(fg)
+    assert close_err(np.concatenate([t1, t2]), want["trace"], tol) <= 1.0
+    assert list(after1) == list(want["after1"])
+    for k in after1:
+        assert update_err(want["before"][k], after1[k], want["after1"][k], tol) <= 1.0, k
+        assert close_err(after2[k], want["after2"][k], tol) <= 1.0, k
+
+
+@pytest.mark.parametrize("product,tol", [("tf32", 1e-3), ("f32", 1e-5)])
+def test_c4_full_size_iteration_against_float64(cg, product, tol):
+    """BASELINE config 4 at FULL size (H = I = 4096, T = 8, B = 1024, dag mode, 1/sqrt(H)-scaled weights): the forward value
+    and every leaf's gradient of one iteration against the float64 restatement (tests/f64_graph.py, pinned to
+    cg_oracle.c in the CPU tier) — the C oracle itself would need an hour on one core for this iteration."""
+    from f64_graph import get_f64
+    B, Hd, T = 1024, 4096, 8
+    scale = 1.0 / np.sqrt(Hd)
+    fd = readme_lstm(get_f64(), Hd, T=T, seed=4, batch=B, d_in=Hd, scale=scale)
+    names = [n for n, _ in fd.leaves()]
+    before = [np.array(v, dtype=np.float32) for _, v in fd.leaves()]
+    td = np.asarray(fd.minimize({}, LR, 1, trace=True))
+    cg.set_mode("dag")
+    cg.set_tf32(product == "tf32")
+    fg = readme_lstm(cg, Hd, T=T, seed=4, batch=B, d_in=Hd, scale=scale)
+    tg = np.asarray(fg.minimize({}, LR, 1, trace=True))
+    assert close_err(tg, td, tol) <= 1.0
+    got = fg.leaves()
+    assert [n for n, _ in got] == names
+    worst = ("", 0.0)
+    for (n, vg), b, (_, vd) in zip(got, before, fd.leaves()):
+        e = update_err(b, vg, vd, tol)
+        if e > worst[1]:
+            worst = (n, e)
+    assert worst[1] <= 1.0, worst

@@ -290,3 +290,39 @@ def test_random_graphs_port_vs_reference_backend_and_exact_vs_dag(oracle):
         oracle.set_mode("exact")
         if not oracle.use_ref("O0"):
             oracle.use_port()
+
+
+@pytest.mark.parametrize("T,batch,d_in,d", [(1, 6, 5, 7), (2, 10, 10, 10), (3, 12, 9, 8), (4, 33, 17, 20)])
+def test_float64_dag_restatement_is_pinned_to_the_oracle(oracle, T, batch, d_in, d):
+    """tests/f64_graph.py (the multithreaded float64 restatement used for full-size parity on the GPU box) against
+    cg_oracle.c's dag mode: same leaf list (names, order, count — so no identity elimination fired in either), same loss
+    trajectory and same leaves after 5 iterations, within f32 rounding of the oracle (1e-5, per element)."""
+    from f64_graph import get_f64
+    from helpers import close_err
+    f64 = get_f64()
+    oracle.set_mode("dag")
+    try:
+        fo = readme_lstm(oracle, d, T=T, seed=70 + T, batch=batch, d_in=d_in)
+        fd = readme_lstm(f64, d, T=T, seed=70 + T, batch=batch, d_in=d_in)
+        to = np.asarray(fo.minimize({}, 0.01, 5, trace=True))
+        td = np.asarray(fd.minimize({}, 0.01, 5, trace=True))
+        assert close_err(to, td, 1e-5) <= 1.0
+        lo, ld = fo.leaves(), fd.leaves()
+        assert [n for n, _ in lo] == [n for n, _ in ld]
+        for (n, vo), (_, vd) in zip(lo, ld):
+            assert close_err(vo, vd, 1e-5) <= 1.0, n
+    finally:
+        oracle.set_mode("exact")
+
+
+def test_close_err_catches_a_wrong_small_entry():
+    """The per-element criterion (helpers.close_err) rejects what the max-norm `rel_err` lets through: a wrong small
+    entry next to one large entry."""
+    from helpers import close_err
+    b = np.full((8, 8), 1e-3, dtype=np.float32)
+    b[0, 0] = 100.0
+    a = b.copy()
+    a[3, 3] = 2e-3                      # 100 % wrong, but 1e-5 of the largest entry
+    assert rel_err(a, b) < 2e-5
+    assert close_err(a, b, 1e-5) > 1.0
+    assert close_err(b * np.float32(1 + 5e-6), b, 1e-5) <= 1.0

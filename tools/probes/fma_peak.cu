@@ -1,0 +1,53 @@
+// fma_peak.cu — measurement probe, NOT part of libcg_b200.so: the FP32 FMA-pipe peak of this GPU, for the roofline
+// denominator of the FP32 SIMT product ("the build must measure both on the box").
+// A register-resident loop of independent FFMA chains: 16 accumulators per thread, 1024 threads per CTA, two CTAs per SM.
+// Built as tools/probes/libcg_probes.so by tools/probes/Makefile; bench.py loads it with ctypes when present.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+namespace {
+constexpr int kChains = 16;
+__global__ void __launch_bounds__(1024, 2) ffma_loop(float* out, int iters, float a, float b) {
+  float acc[kChains];
+#pragma unroll
+  for (int c = 0; c < kChains; c++) acc[c] = (float)(threadIdx.x + c);
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int c = 0; c < kChains; c++) acc[c] = fmaf(acc[c], a, b);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int c = 0; c < kChains; c++) s += acc[c];
+  if (s == 12345.678f) out[0] = s;  // keeps the loop alive without a store in the common case
+}
+}  // namespace
+
+// TFLOP/s of the best of `reps` launches (each about `iters` x 16 FFMA per thread), on the current device.
+extern "C" double cg_probe_fma_tflops(int iters, int reps) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1.0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  float* out = nullptr;
+  if (cudaMalloc(&out, 4) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int grid = sms * 2, threads = 1024;
+  ffma_loop<<<grid, threads>>>(out, 64, 0.999f, 0.001f);  // warm-up
+  double best = 0.0;
+  for (int r = 0; r < reps; r++) {
+    cudaEventRecord(e0);
+    ffma_loop<<<grid, threads>>>(out, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * kChains * (double)iters * threads * grid;
+    best = std::max(best, flop / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}

@@ -147,6 +147,8 @@ constexpr int DP_MAX_WORLD = 8;
 constexpr int DP_THREADS = 512;
 constexpr int DP_DEFAULT_CTAS = 64;  // CG_DP_CTAS overrides
 int dp_max_ctas();
+constexpr int DP_MC_DEFAULT_CTAS = 32;  // in-switch exchange; CG_DP_MC_CTAS overrides
+int dp_mc_max_ctas();
 constexpr unsigned long long DP_WAIT_TIMEOUT_NS = 20000000000ull;  // default 20 s (CG_DP_TIMEOUT_MS): a lost rank raises an error, never hangs the GPU
 enum { DP_FLAG_A = 0, DP_FLAG_B = 16, DP_FLAG_EPOCH = 32, DP_FLAG_TICKET = 33, DP_FLAG_ERR = 34, DP_FLAG_WORDS = 64 };
 struct DpReduceArgs {

@@ -270,6 +270,17 @@ int dp_max_ctas() {
   return v;
 }
 
+// The in-switch kernel only pulls n / world bytes and pushes n / world bytes per rank, so a small grid saturates the link
+// (measured at 2 ranks: 32 CTAs and 64 CTAs take the same 190 us per 64 MB weight) and leaves the SMs to the products.
+int dp_mc_max_ctas() {
+  static const int v = [] {
+    const char* e = getenv("CG_DP_MC_CTAS");
+    const int n = e ? atoi(e) : DP_MC_DEFAULT_CTAS;
+    return n < 1 ? 1 : n > kNumSMs ? kNumSMs : n;
+  }();
+  return v;
+}
+
 void launch_dp_multimem_update(const DpMcArgs& a, cudaStream_t stream) {
   if (a.n == 0) return;
   if (a.n % 4) throw Error("internal: fused data-parallel update needs a multiple of 4 elements");
@@ -278,7 +289,7 @@ void launch_dp_multimem_update(const DpMcArgs& a, cudaStream_t stream) {
   const size_t slice4 = (a.n / 4 + a.world - 1) / a.world;
   const int unroll = a.world <= 2 ? 4 : 2;
   size_t grid = (slice4 + (size_t)DP_THREADS * unroll - 1) / ((size_t)DP_THREADS * unroll);
-  if (grid > (size_t)dp_max_ctas()) grid = dp_max_ctas();
+  if (grid > (size_t)dp_mc_max_ctas()) grid = dp_mc_max_ctas();
   if (grid < 1) grid = 1;
   if (unroll == 4) dp_multimem_update_kernel<4><<<(unsigned)grid, DP_THREADS, 0, stream>>>(a);
   else dp_multimem_update_kernel<2><<<(unsigned)grid, DP_THREADS, 0, stream>>>(a);

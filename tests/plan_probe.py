@@ -63,6 +63,15 @@ def main():
             for fused in (0, 1):
                 assert lib.cg_dp_plan_only(2, fused) == 0
                 record(f"c4_hoist{hoist}_dp2_{'fused' if fused else 'nccl'}", f, 0.01, describe=True)
+            if hoist:
+                # 8 ranks with the in-switch exchange (fused = 2): same tape, every exchange through the multicast heap
+                assert lib.cg_dp_plan_only(8, 2) == 0
+                record("c4_dp8_multimem", f, 0.01, describe=True)
+                # exact mode runs as replicas: no exchange is ever planned (its in-line SGD is interleaved with the walk)
+                api.set_mode("exact")
+                assert lib.cg_dp_plan_only(2, 1) == 0
+                record("c3_exact_dp2", readme_lstm(api, 30), 0.01)
+                api.set_mode("dag")
             assert lib.cg_dp_plan_only(1, 0) == 0
     try:
         x.minimize({}, 0.01, 1)

@@ -102,6 +102,21 @@ def test_data_parallel_tape(plans):
             assert ex[0] > 69
 
 
+def test_data_parallel_in_switch_tape_and_exact_mode_replicas(plans):
+    """From three ranks up the exchange is planned through the multicast heap (NVLS): the same 69 fused exchanges, every
+    one marked `multimem`, with the gradient slots in an arena of their own. Exact mode under data parallelism plans NO
+    exchange at all — C1-C3 and the tree walk run as replicas, the sum would multiply every update."""
+    mc, ipc = plans["c4_dp8_multimem"], plans["c4_hoist1_dp2_fused"]
+    assert (mc["allreduces"], mc["dp_fused_updates"], mc["dp_multimem_updates"]) == (0, 69, 69)
+    assert ipc["dp_multimem_updates"] == 0
+    ex = [l for l in mc["kernels"] if "DPUPDATE" in l]
+    assert len(ex) == 69 and all(l.endswith("multimem") for l in ex)
+    assert mc["arena_bytes"] == ipc["arena_bytes"]  # same slots, split over two arenas
+    rep = plans["c3_exact_dp2"]
+    assert (rep["allreduces"], rep["dp_fused_updates"]) == (0, 0)
+    assert rep["kernels_per_iter"] == plans["c3_d30_exact"]["kernels_per_iter"]
+
+
 def test_random_graphs_plan_and_compile():
     """tests/plan_fuzz.py: random expression trees (every operator, scalar / matrix mixes, broadcasts, scalar <- matrix
     means, square products) plan in both modes with and without hoisting — the hoisting pass re-verifies every

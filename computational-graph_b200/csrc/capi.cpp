@@ -194,6 +194,14 @@ void cg_set_mode(int m) { guard_rc([&] { Runtime::get().mode = m; }); }
 void cg_set_tf32(int v) { guard_rc([&] { Runtime::get().tf32 = v; }); }
 void cg_set_fix_act_grad(int v) { guard_rc([&] { Runtime::get().fix_act_grad = v; }); }
 void cg_set_fuse(int v) { guard_rc([&] { Runtime::get().fuse = v; }); }
+void cg_set_fix_broadcast_sum(int v) {
+  guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    if (rt.fix_broadcast_sum != v) rt.dp_epoch++;  // the backward tape changes: invalidate cached plans
+    rt.fix_broadcast_sum = v;
+  });
+}
+void cg_set_fix_sub_sign(int v) { guard_rc([&] { Runtime::get().fix_sub_sign = v; }); }  // construction-time rule
 // (these three choices are baked into a compiled plan — its captured graphs, its kernel choice and its resident-executor
 // eligibility — so a change invalidates the cached plans, like every other setter below)
 void cg_set_cuda_graph(int v) {

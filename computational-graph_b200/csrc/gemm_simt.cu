@@ -95,7 +95,7 @@ __device__ __forceinline__ void store_tile(float (*S)[BM + PAD], const float (&r
 }
 
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(256) gemm_tiled_kernel(const float* __restrict__ A, const float* __restrict__ B,
+__global__ void __launch_bounds__(256, 2) gemm_tiled_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                          float* __restrict__ C, int m, int n, int k, int lda, int ldb,
                                                          int ldc, GemmEpilogue epi) {
   __shared__ __align__(16) float As[2][BK][BM + PAD];

@@ -303,6 +303,8 @@ static Function* fold_constant(Function* g);
 
 Function* make_binary(Kind kind, const Function& a, const Function& b) {
   const float identity = kind == Kind::Mul ? 1.0f : 0.0f;  // ops.rs:338-343 (Sub shares Add's rule, Q4)
+  // corrected semantics (cg_set_fix_sub_sign): 0 - x keeps its sign
+  if (kind == Kind::Sub && Runtime::get().fix_sub_sign && value_all_equal(a.value, identity)) return make_unary(Kind::Neg, b);
   if (value_all_equal(a.value, identity)) return clone_function(b);  // ops.rs:255-259
   if (value_all_equal(b.value, identity)) return clone_function(a);
   auto* g = new Function();

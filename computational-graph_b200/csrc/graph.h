@@ -85,6 +85,8 @@ struct Runtime {
   int mode = 0;          // 0 = exact (the reference's tree walk), 1 = dag (memoised)
   int tf32 = 0;          // 0 = FP32 SIMT products, 1 = tcgen05 TF32 where eligible
   int fix_act_grad = 0;  // 0 = reproduce Q3
+  int fix_broadcast_sum = 0;  // 0 = reproduce Q5 in the backward pass (scalar <- matrix error = mean); 1: sum
+  int fix_sub_sign = 0;       // 0 = reproduce Q4's `0 - x -> x`; 1: `0 - x -> -x`
   int fuse = 1;          // 0 = one kernel per IR instruction (debug / ablation)
   int use_graph = 1;     // capture each iteration as a CUDA graph
   int graph_streams = 4; // side streams used when an iteration is captured as a DAG (0 = single stream)

@@ -75,6 +75,8 @@ struct Builder {
   std::unordered_set<const float*> seen_input_bufs;
 
   bool dp = false;
+  bool in_backward = false;      // set around the backward walk: only there does fix_broadcast_sum apply
+  int fix_broadcast_sum = 0;
 
   Builder(Plan& plan, float lr_, int fix) : p(plan), lr(lr_), fix_act_grad(fix), dp(dp_enabled()) {}
 
@@ -127,7 +129,14 @@ struct Builder {
   }
 
   // ---- Constant dispatch tables as emitters ---------------------------------------------------------------
-  int avg(int a) { return sh(a).m ? emit(IOp::Avg, Shape{}, a) : a; }  // ops.rs:430-442
+  // ops.rs:430-442. Corrected semantics (cg_set_fix_broadcast_sum): in the backward pass a scalar absorbing a matrix
+  // error takes the SUM (imm = the divisor: 1) — the gradient of a broadcast scalar — instead of the reference's mean.
+  int avg(int a) {
+    if (!sh(a).m) return a;
+    const int v = emit(IOp::Avg, Shape{}, a);
+    if (in_backward && fix_broadcast_sum) p.tape.back().imm = 1.0f;
+    return v;
+  }
 
   static IOp unary_iop(UOp op, bool matrix_semantics) {
     switch (op) {
@@ -1042,6 +1051,7 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root, bool 
 
   if (p.mode == 1 && !forward_only && dp_multimem_active() && migrate_dp_weights(root)) root.eval_plan.reset();
   Builder b(p, lr, rt.fix_act_grad);
+  b.fix_broadcast_sum = rt.fix_broadcast_sum;
   b.forward(root);
   const Shape rsh = Builder::shape_of(root);
   p.root_n = rsh.n();
@@ -1068,6 +1078,7 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root, bool 
   // optimize.rs:69 — `let mut error = self.value_mut().copy_and_fill(1.)`
   if (!forward_only) {
     int error = b.emit(IOp::Fill, rsh, -1, -1, 1.0f);
+    b.in_backward = true;
     if (p.mode == 0) b.backprop_tree(root, error);
     else b.backprop_dag(root, error);
   }
@@ -1121,6 +1132,7 @@ void build_vm(Plan& p) {
     } else if (s.kind == Step::AVG) {
       const Val& a = p.vals[s.ins.a];
       if (a.sh.n() > kStrictReduceMax || a.sh.n() > max_elems) return;
+      if (s.ins.imm > 0.0f) return;  // a sum instead of a mean (corrected semantics): the CUDA-graph executor has it
       elems_seen = std::max(elems_seen, a.sh.n());
       v.kind = VmStep::AVG;
       v.n = (int)a.sh.n();
@@ -1210,7 +1222,8 @@ void plan_launch_step(Plan& p, size_t index, cudaStream_t stream) {
         break;
       case Step::AVG: {
         const Val& a = p.vals[s.ins.a];
-        launch_reduce_avg(a.ptr, a.sh.n(), p.vals[s.ins.dst].ptr, rt.red_ws, stream);
+        if (s.ins.imm > 0.0f) launch_reduce_div(a.ptr, a.sh.n(), s.ins.imm, p.vals[s.ins.dst].ptr, rt.red_ws, stream);
+        else launch_reduce_avg(a.ptr, a.sh.n(), p.vals[s.ins.dst].ptr, rt.red_ws, stream);
       } break;
       case Step::GEMM: {
         const Val &a = p.vals[s.ins.a], &b = p.vals[s.ins.b], &c = p.vals[s.ins.dst];

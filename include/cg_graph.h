@@ -95,6 +95,12 @@ int cg_kind(const cg_function *f);
 void cg_set_mode(int mode);           /* 0 = exact (the reference's tree walk), 1 = dag (memoised, visit-once) */
 void cg_set_tf32(int on);             /* 1: tcgen05 TF32 tensor-core products for eligible shapes */
 void cg_set_fix_act_grad(int on);     /* 1: sigmoid/tanh pass error*derivative (repairs Q3) */
+/* Corrected-semantics switches, each off by default so that the reference is reproduced:
+ * broadcast_sum: in the backward pass a scalar that absorbs a matrix-shaped error takes its SUM (the gradient of a
+ *   broadcast scalar; the root error is ones, so the loss is the sum of the root's elements) instead of the reference's
+ *   mean (Q5: src/ops.rs:79-80,103-104,126-134); sub_sign: `0 - x` builds `-x` instead of `x` (Q4: src/ops.rs:255-263). */
+void cg_set_fix_broadcast_sum(int on);
+void cg_set_fix_sub_sign(int on);
 void cg_set_fuse(int on);             /* 0: one kernel per tape instruction (ablation) */
 void cg_set_cuda_graph(int on);       /* 0: launch kernels eagerly instead of replaying a CUDA graph */
 void cg_set_strict_gemm_max(int dim); /* products with max(m,n,k) <= dim use the bit-exact kernel */

@@ -320,7 +320,15 @@ static void c_free(Constant *c) {
   if (c->is_matrix && c->m.array) OPS.free_matrix(&c->m);
   c->m.array = NULL;
 }
+/* Corrected-semantics switches (defaults reproduce the reference):
+ *   FIX_BROADCAST_SUM: in the BACKWARD pass a scalar that absorbs a matrix-shaped error takes its SUM — the gradient of
+ *     the loss (root error == ones, i.e. the sum of the root's elements) with respect to a broadcast scalar — instead
+ *     of the mean the reference's S<-M rule gives it (Q5; ops.rs:79-80,103-104,126-134). The forward pass keeps the mean:
+ *     there it is the value-shape rule, not a gradient.
+ *   FIX_SUB_SIGN: `0 - x` is `-x`; the reference shares Add's identity rule and returns `x` (Q4; ops.rs:255-263). */
+static int FIX_BROADCAST_SUM = 0, FIX_SUB_SIGN = 0, IN_BACKWARD = 0;
 static float m_avg(const Matrix *m) { /* ops.rs:438-442 */
+  if (FIX_BROADCAST_SUM && IN_BACKWARD) return OPS.reduce_sum(m);
   return OPS.reduce_sum(m) / (float)((size_t)m->height * m->width);
 }
 static float c_avg(const Constant *c) { return c->is_matrix ? m_avg(&c->m) : c->s; } /* ops.rs:430-435 */
@@ -447,6 +455,8 @@ static long COUNT_GEMM = 0, COUNT_OPS = 0;
 
 void orc_set_mode(int m) { MODE = m; }
 void orc_set_fix_act_grad(int v) { FIX_ACT_GRAD = v; }
+void orc_set_fix_broadcast_sum(int v) { FIX_BROADCAST_SUM = v; }
+void orc_set_fix_sub_sign(int v) { FIX_SUB_SIGN = v; }
 long orc_count_gemm(void) { return COUNT_GEMM; }
 void orc_reset_counts(void) { COUNT_GEMM = COUNT_OPS = 0; }
 
@@ -577,6 +587,7 @@ static void forward(Function *f, int nargs, const char **names, const Constant *
 static Function *make_binary(int kind, const Function *a, const Function *b) {
   ensure_ops();
   float identity = kind == K_MUL ? 1.0f : 0.0f; /* ops.rs:338-343; Sub shares Add's rule: 0 - x -> x (Q4) */
+  if (FIX_SUB_SIGN && kind == K_SUB && c_all_equal(&a->value, identity)) return orc_neg(b);
   if (c_all_equal(&a->value, identity)) return orc_clone(b); /* ops.rs:255-259 */
   if (c_all_equal(&b->value, identity)) return orc_clone(a);
   /* value-shape rule, ops.rs:218-228 */
@@ -882,6 +893,7 @@ static int run_minimize(Function *f, int nargs, const char **names, const Consta
       else trace[i] = f->value.s;
     }
     Constant error = c_copy_and_fill(&f->value, 1.0f); /* :69 — allocated every iteration (Q11) */
+    IN_BACKWARD = 1;
     if (MODE == 0) {
       backprop_tree(f, &error, lr);
       c_free(&error);
@@ -900,6 +912,7 @@ static int run_minimize(Function *f, int nargs, const char **names, const Consta
     } else {
       c_free(&error);
     }
+    IN_BACKWARD = 0;
   }
   free(order.v);
   return 0;

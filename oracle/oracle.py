@@ -38,6 +38,8 @@ class OracleApi(Api):
         lib.orc_tree_size.restype = ctypes.c_long
         lib.orc_tree_size.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_long)]
         lib.orc_set_fix_act_grad.argtypes = [ctypes.c_int]
+        lib.orc_set_fix_broadcast_sum.argtypes = [ctypes.c_int]
+        lib.orc_set_fix_sub_sign.argtypes = [ctypes.c_int]
 
     def use_ref(self, which: str = "O0") -> bool:
         """Route every matrix op through the reference-compiled CPU backend. Returns False when

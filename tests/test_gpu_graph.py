@@ -565,3 +565,35 @@ def test_print_freq_loss_log(cg, capfd, executor):
     for k, it in enumerate((1, 3, 5)):
         rows = np.array([[float(x) for x in out[2 * k + r].split()] for r in range(2)], dtype=np.float32)
         assert np.allclose(rows, tr[it], rtol=1e-5), (it, rows, tr[it])
+
+
+def test_corrected_broadcast_sum_and_sub_sign_match_the_oracle(cg, oracle):
+    """The same two switches on the CUDA path against the oracle (which the CPU tier checks against finite differences):
+    bit-exact, no transcendental is involved. The sum takes the CUDA-graph executor (the resident one keeps the mean)."""
+    B = np.array([[0.5, -1.0, 2.0], [0.25, 1.5, -0.75]], dtype=np.float32)
+
+    def build(api):
+        x = api.Function.scalar_param("x", 0.3)
+        return ((x * api.Function.scalar(3.0) + api.Function.constant(api.Constant(B))).sq() + api.Function.scalar(0.5)).sq()
+
+    cg.set_fix_broadcast_sum(True)
+    oracle.lib.orc_set_fix_broadcast_sum(1)
+    try:
+        fg, fo = build(cg), build(oracle)
+        tg = np.asarray(fg.minimize({}, 1e-3, 5, trace=True))
+        to = np.asarray(fo.minimize({}, 1e-3, 5, trace=True))
+        assert np.array_equal(tg.view(np.int32), to.view(np.int32))
+        assert np.float32(fg.leaves()[0][1]) == np.float32(fo.leaves()[0][1])
+        assert cg.plan_stats(fg, 1e-3)["vm_resident"] == 0
+    finally:
+        cg.set_fix_broadcast_sum(False)
+        oracle.lib.orc_set_fix_broadcast_sum(0)
+    for fix, want in ((False, 0.4), (True, 0.6)):
+        cg.set_fix_sub_sign(fix)
+        try:
+            m = cg.Function.param("m", cg.Constant(np.full((2, 2), 0.5, dtype=np.float32)))
+            f = cg.Function.constant(cg.Constant(np.zeros((2, 2), dtype=np.float32))) - m
+            f.minimize({}, 0.1, 1)
+            assert np.allclose(np.asarray(f.leaves()[0][1]), want)
+        finally:
+            cg.set_fix_sub_sign(False)

@@ -326,3 +326,48 @@ def test_close_err_catches_a_wrong_small_entry():
     assert rel_err(a, b) < 2e-5
     assert close_err(a, b, 1e-5) > 1.0
     assert close_err(b * np.float32(1 + 5e-6), b, 1e-5) <= 1.0
+
+
+def test_corrected_broadcast_sum_and_sub_sign_match_finite_differences(oracle):
+    """SURVEY §8f-2, the two other corrected-semantics switches, each against central finite differences of the loss the
+    loop actually descends: L = sum of the root's elements (the root error is ones, src/optimize.rs:69).
+      * broadcast_sum: a scalar under a matrix-shaped error receives the SUM of it (d L / d x), not the reference's mean;
+      * sub_sign: `0 - x` is `-x` (the reference's shared identity rule turns it into `x`, Q4)."""
+    F, Cn = oracle.Function, oracle.Constant
+    B = np.array([[0.5, -1.0, 2.0], [0.25, 1.5, -0.75]], dtype=np.float32)
+    lr = 1e-3
+
+    def build(x0):
+        x = F.scalar_param("x", x0)
+        return ((x * F.scalar(3.0) + F.constant(Cn(B))).sq() + F.scalar(0.5)).sq()  # x is used ONCE (each use is its own leaf, Q1)
+
+    def loss(x0):
+        f = build(x0)
+        return float(np.sum(np.asarray(f.minimize({}, lr, 1, trace=True), dtype=np.float64)))
+
+    x0, h = 0.3, 1e-3
+    fd = (loss(x0 + h) - loss(x0 - h)) / (2 * h)
+    got = {}
+    for fix in (0, 1):
+        oracle.lib.orc_set_fix_broadcast_sum(fix)
+        try:
+            f = build(x0)
+            f.minimize({}, lr, 1)
+            got[fix] = (x0 - float(f.leaves()[0][1])) / lr
+        finally:
+            oracle.lib.orc_set_fix_broadcast_sum(0)
+    # the leaf sits under nested matrix errors, so the reference's means compound; the corrected sum is the derivative
+    assert abs(got[1] - fd) <= 2e-3 * abs(fd)
+    assert abs(got[0] - fd) > 0.5 * abs(fd)
+
+    def step(fix):
+        oracle.lib.orc_set_fix_sub_sign(fix)
+        try:
+            m = F.param("m", Cn(np.full((2, 2), 0.5, dtype=np.float32)))
+            f = F.constant(Cn(np.zeros((2, 2), dtype=np.float32))) - m
+            f.minimize({}, 0.1, 1)
+            return np.asarray(f.leaves()[0][1])
+        finally:
+            oracle.lib.orc_set_fix_sub_sign(0)
+    assert np.allclose(step(0), 0.4)   # reference: 0 - m IS m, so m descends
+    assert np.allclose(step(1), 0.6)   # corrected: d(sum(-m))/dm = -1, so m ascends

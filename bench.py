@@ -345,7 +345,7 @@ def measure_peaks(torch, rows_list):
 # ---------------------------------------------------------------------------------------------------------
 # parity of the data-parallel path, checked inside the bench run (N > 1), before anything is timed
 # ---------------------------------------------------------------------------------------------------------
-def dp_parity(api, pkg, torch, dist, rank, world, local_rank, multimem):
+def dp_parity(api, pkg, torch, dist, rank, world, local_rank, multimem, tf32_batch=None, scale_lr=True):
     """The sharded run with every weight through the fused exchange, against (a) the same kernels on ONE GPU over the
     full batch and (b) the CPU oracle (dag mode). One f32 shape (1e-5) and one TF32 shape (1e-3; against the f32 oracle
     only the first iteration is held to it — TF32 rounding is amplified from iteration to iteration on one GPU as on
@@ -355,8 +355,16 @@ def dp_parity(api, pkg, torch, dist, rank, world, local_rank, multimem):
     from helpers import close_err
     from oracle.oracle import get_oracle
 
-    cases = [{"name": "f32", "tf32": 0, "batch": 16 * world, "hidden": 48, "inp": 40, "T": 3, "iters": 4, "tol": 1e-5},
-             {"name": "tf32", "tf32": 1, "batch": 256 * world, "hidden": 256, "inp": 256, "T": 3, "iters": 3, "tol": 1e-3}]
+    # The reference's rules make the weight update grow with the batch (root error == 1, no normalisation, and Q3 hands
+    # every gate the local derivative): at lr = .01 a 2048-row batch moves a 1/16-scale weight by several times its size
+    # per iteration, and the 1e-7 that a different summation order leaves behind is amplified a thousandfold within
+    # three iterations — on one GPU exactly as on eight. The check is about the EXCHANGE, so the learning rate shrinks
+    # with the batch (same dynamics at every world size), and the first iteration — where both runs start from identical
+    # weights and differ by the exchange alone — is held to the tolerance separately, gradients included.
+    tb = tf32_batch or 256 * world
+    cases = [{"name": "f32", "tf32": 0, "batch": 16 * world, "hidden": 48, "inp": 40, "T": 3, "iters": 4, "tol": 1e-5, "lr": LR},
+             {"name": "tf32", "tf32": 1, "batch": tb, "hidden": 256, "inp": 256, "T": 3, "iters": 3, "tol": 1e-3,
+              "lr": LR * 256.0 / tb if scale_lr else LR}]
     out = {"cases": [], "criterion": "max over elements of |a-b| / (tol*|b| + tol*rms(b)) <= 1"}
     api.set_mode("dag")
     for c in cases:
@@ -371,25 +379,39 @@ def dp_parity(api, pkg, torch, dist, rank, world, local_rank, multimem):
         tgt = rng.uniform(-.1, .1, (c["batch"], c["hidden"])).astype(np.float32)
         p_r, x_r, t_r = shard_lstm_problem(params, xs, tgt, rank, world)
         f = lstm_loss(api, [api.Constant(x) for x in x_r], api.Constant(t_r), p_r)
-        st = api.plan_stats(f, LR)
+        lr = c["lr"]
+        st = api.plan_stats(f, lr)
         exchange = api.dp_exchange_name()
-        tr = np.array(f.minimize({}, LR, c["iters"], trace=True))
+        tr1 = np.array(f.minimize({}, lr, 1, trace=True))
+        dp_first = [(n, np.array(v)) for n, v in f.leaves()]
+        tr = np.concatenate([tr1, np.array(f.minimize({}, lr, c["iters"] - 1, trace=True))])
         dp_leaves = [(n, np.array(v)) for n, v in f.leaves()]
         del f
         api.dp_shutdown()  # the communicator is gone: the next plan has no exchange in it
         api.dp_set_fused_min(-1)
         fs = lstm_loss(api, [api.Constant(x) for x in xs], api.Constant(tgt), params)
-        ts = np.array(fs.minimize({}, LR, c["iters"], trace=True))
+        ts1 = np.array(fs.minimize({}, lr, 1, trace=True))
+        single_first = [(n, np.array(v)) for n, v in fs.leaves()]
+        ts = np.concatenate([ts1, np.array(fs.minimize({}, lr, c["iters"] - 1, trace=True))])
         single_leaves = [(n, np.array(v)) for n, v in fs.leaves()]
         del fs
         orc = get_oracle()
         orc.use_port()
         orc.set_mode("dag")
         fo = lstm_loss(orc, [orc.Constant(x) for x in xs], orc.Constant(tgt), params)
-        to = np.asarray(fo.minimize({}, LR, c["iters"], trace=True))
+        to = np.asarray(fo.minimize({}, lr, c["iters"], trace=True))
         orc.set_mode("exact")
         lo, hi = row_block(c["batch"], rank, world)
         tol = c["tol"]
+        # first iteration: forward value and every leaf's update (p0 - p1) / lr, the exchanged gradients among them
+        first = close_err(tr1, ts1[:, lo:hi, :], tol)
+        for (n, vg), (ns, vs) in zip(dp_first, single_first):
+            p0 = params[n][lo:hi] if n in ROW_LOCAL else params[n]
+            want = vs[lo:hi] if n in ROW_LOCAL else vs
+            gg, gw = (p0.astype(np.float64) - vg) / lr, (p0.astype(np.float64) - want) / lr
+            noise = 4 * np.finfo(np.float32).eps * np.maximum(np.abs(p0), 1e-30) / lr
+            bound = tol * np.abs(gw) + tol * max(float(np.sqrt(np.mean(gw * gw))), 1e-30) + noise
+            first = max(first, float(np.max(np.abs(gg - gw) / bound)))
         vs_single = close_err(tr, ts[:, lo:hi, :], tol)
         for (n, vg), (ns, vs) in zip(dp_leaves, single_leaves):
             vs_single = max(vs_single, close_err(vg, vs[lo:hi] if n in ROW_LOCAL else vs, tol))
@@ -399,13 +421,15 @@ def dp_parity(api, pkg, torch, dist, rank, world, local_rank, multimem):
             vs_oracle = close_err(tr, to[:, lo:hi, :], tol)
             for (n, vg), (no, vo) in zip(dp_leaves, fo.leaves()):
                 vs_oracle = max(vs_oracle, close_err(vg, np.asarray(vo)[lo:hi] if n in ROW_LOCAL else np.asarray(vo), tol))
-        t = torch.tensor([vs_single, vs_oracle], dtype=torch.float64, device="cuda")
+        t = torch.tensor([vs_single, vs_oracle, first], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        out["cases"].append({"case": f"{c['name']}: LSTM B={c['batch']} H={c['hidden']} I={c['inp']} T={c['T']}, {c['iters']} iterations",
+        out["cases"].append({"case": f"{c['name']}: LSTM B={c['batch']} H={c['hidden']} I={c['inp']} T={c['T']}, {c['iters']} iterations, lr={lr:g}",
                              "tol": tol, "worst_vs_single_gpu": float(t[0]), "worst_vs_oracle": float(t[1]),
+                             "worst_first_iteration_vs_single_gpu": float(t[2]),
                              "fused_exchanges_per_iter": st["dp_fused_updates"], "in_switch": st["dp_multimem_updates"],
                              "nccl_allreduces_per_iter": st["allreduces"], "exchange": exchange})
-    out["ok"] = all(c["worst_vs_single_gpu"] <= 1.0 and c["worst_vs_oracle"] <= 1.0 for c in out["cases"])
+    out["ok"] = all(c["worst_vs_single_gpu"] <= 1.0 and c["worst_vs_oracle"] <= 1.0 and c["worst_first_iteration_vs_single_gpu"] <= 1.0
+                    for c in out["cases"])
     out["max_rel_err"] = max(max(c["worst_vs_single_gpu"], c["worst_vs_oracle"]) * c["tol"] for c in out["cases"])
     out["tol"] = {c["case"].split(":")[0]: c["tol"] for c in out["cases"]}
     out["exchange"] = out["cases"][0]["exchange"]
@@ -612,6 +636,9 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="N = 1: skip the secondary configs and the same-config block")
     ap.add_argument("--no-same-config", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the data-parallel parity check before timing")
+    ap.add_argument("--parity-only", action="store_true", help="N > 1: run the parity check, print it, time nothing")
+    ap.add_argument("--parity-tf32-batch", type=int, default=0, help="(experiments) global batch of the TF32 parity case")
+    ap.add_argument("--parity-fixed-lr", action="store_true", help="(experiments) do not shrink the parity learning rate with the batch")
     ap.add_argument("--multimem", default="auto", choices=["auto", "on", "off"],
                     help="N > 1: in-switch (NVLS multimem) weight exchange — auto: from three ranks up")
     args = ap.parse_args()
@@ -637,7 +664,13 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         if not args.no_parity:
-            parity = dp_parity(api, pkg, torch, dist, rank, world, local_rank, args.multimem)
+            parity = dp_parity(api, pkg, torch, dist, rank, world, local_rank, args.multimem,
+                               tf32_batch=args.parity_tf32_batch or None, scale_lr=not args.parity_fixed_lr)
+            if args.parity_only:
+                if rank == 0:
+                    print(json.dumps({"n_gpus": world, "parity": parity}))
+                dist.destroy_process_group()
+                sys.exit(0 if parity["ok"] else 1)
             if not parity["ok"]:
                 if rank == 0:
                     print(json.dumps({"metric": METRIC, "error": "data-parallel parity check failed; nothing was timed",

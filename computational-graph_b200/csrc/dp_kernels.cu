@@ -287,7 +287,11 @@ void launch_dp_multimem_update(const DpMcArgs& a, cudaStream_t stream) {
   // The switch does the summing, so few threads keep the link busy: a rank only PULLS n / world bytes (the rest of its
   // inbound traffic is its peers' posted multicast stores). Two loads per thread from 3 ranks on, four at 2 ranks.
   const size_t slice4 = (a.n / 4 + a.world - 1) / a.world;
-  const int unroll = a.world <= 2 ? 4 : 2;
+  static const int forced_unroll = [] {
+    const char* e = getenv("CG_DP_MC_UNROLL");
+    return e ? atoi(e) : 0;
+  }();
+  const int unroll = forced_unroll == 2 || forced_unroll == 4 ? forced_unroll : (a.world <= 2 ? 4 : 2);
   size_t grid = (slice4 + (size_t)DP_THREADS * unroll - 1) / ((size_t)DP_THREADS * unroll);
   if (grid > (size_t)dp_mc_max_ctas()) grid = dp_mc_max_ctas();
   if (grid < 1) grid = 1;

@@ -131,6 +131,8 @@ void capture_nodes(Plan& p, Runtime& rt, std::vector<CapNode>& nodes, cudaGraph_
   // dependencies from memory locations (RAW, WAR, WAW), in program order
   std::unordered_map<const float*, Loc> loc;
   std::vector<std::vector<int>> deps(n);
+  int lane_prev[kIoLanes];
+  for (int& l : lane_prev) l = -1;
   for (size_t i = 0; i < n; i++) {
     const CapNode& io = nodes[i];
     auto add = [&](int d) {
@@ -148,6 +150,35 @@ void capture_nodes(Plan& p, Runtime& rt, std::vector<CapNode>& nodes, cudaGraph_
       l.last_writer = (int)i;
       l.readers.clear();
     }
+    // lanes stay in order: every rank must issue the exchanges of one communicator in the same order, and the inputs
+    // are copied in the order the iteration needs them
+    if (io.lane >= 0 && io.lane < kIoLanes) {
+      add(lane_prev[io.lane]);
+      lane_prev[io.lane] = (int)i;
+    }
+  }
+  // Transitive reduction: a dependency that is already an ancestor of another dependency of the same node adds an edge
+  // and nothing else. The memory-derived sets above are full of those (every reader of a leaf depends on its last writer
+  // AND on whatever that writer's other readers depended on), and what a graph launch costs the host grows with its edges:
+  // for config 5 (~1000 nodes) an unreduced launch took ~45 ms of CPU time — invisible while launches queue up behind one
+  // another, fully exposed in a `minimize(&args, lr, 1)` call, which waits for its result.
+  {
+    const size_t words = (n + 63) / 64;
+    std::vector<uint64_t> anc(n * words, 0);  // anc[i]: every node i transitively depends on
+    for (size_t i = 0; i < n; i++) {
+      std::vector<int>& d = deps[i];
+      std::sort(d.begin(), d.end(), std::greater<int>());  // nearest first: the likeliest to cover the others
+      std::vector<int> kept;
+      uint64_t* mine = &anc[i * words];
+      for (int dep : d) {
+        if (mine[(size_t)dep / 64] >> ((size_t)dep % 64) & 1) continue;  // reachable through a dependency already kept
+        kept.push_back(dep);
+        const uint64_t* theirs = &anc[(size_t)dep * words];
+        for (size_t w = 0; w < words; w++) mine[w] |= theirs[w];
+        mine[(size_t)dep / 64] |= (uint64_t)1 << ((size_t)dep % 64);
+      }
+      d.swap(kept);
+    }
   }
   {
     // Exact DAG: everything is captured on ONE stream whose capture dependency set is replaced, before every node,
@@ -156,8 +187,6 @@ void capture_nodes(Plan& p, Runtime& rt, std::vector<CapNode>& nodes, cudaGraph_
     // behind it on the same stream — with side streams that cost 2.0 ms of a C4 iteration fed from the host.
     std::vector<std::vector<cudaGraphNode_t>> after(n);  // the dependency set of the stream after node i
     std::vector<char> has_succ(n, 0);
-    int lane_last[kIoLanes];
-    for (int& l : lane_last) l = -1;
     CG_CUDA(cudaStreamBeginCapture(rt.stream, cudaStreamCaptureModeThreadLocal));
     try {
       for (size_t i = 0; i < n; i++) {
@@ -168,10 +197,6 @@ void capture_nodes(Plan& p, Runtime& rt, std::vector<CapNode>& nodes, cudaGraph_
             if (std::find(d.begin(), d.end(), g) == d.end()) d.push_back(g);
         };
         for (int dep : deps[i]) add_after(dep);
-        // lanes stay in order: every rank must issue the exchanges of one communicator in the same order, and the
-        // inputs are copied in the order the iteration needs them
-        const int lane = nodes[i].lane;
-        if (lane >= 0 && lane < kIoLanes && lane_last[lane] >= 0) add_after(lane_last[lane]);
         CG_CUDA(cudaStreamUpdateCaptureDependencies(rt.stream, d.empty() ? nullptr : d.data(), d.size(), cudaStreamSetCaptureDependencies));
         nodes[i].launch(rt.stream);
         cudaStreamCaptureStatus status;
@@ -180,7 +205,6 @@ void capture_nodes(Plan& p, Runtime& rt, std::vector<CapNode>& nodes, cudaGraph_
         CG_CUDA(cudaStreamGetCaptureInfo(rt.stream, &status, nullptr, nullptr, &cur, &ncur));
         if (status != cudaStreamCaptureStatusActive) throw Error("internal: stream capture was invalidated");
         after[i].assign(cur, cur + ncur);
-        if (lane >= 0 && lane < kIoLanes) lane_last[lane] = (int)i;
       }
       // end on the join of every sink
       std::vector<cudaGraphNode_t> sinks;

@@ -629,10 +629,14 @@ void launch_pair_variant(const CUtensorMap& ma, const CUtensorMap& mb_big, const
   CG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_pair_kernel<A_MN, B_MN>, ma, mb_big, mb_small, C, m, n, k, ldc, epi.mode, epi.lr, wmax));
 }
 
-// Off by default: measured on B200 (tools/gemm_sweep.py) the pair kernel's main loop is marginally faster per k-block
-// (0.356 vs 0.374 us) but its fixed cost (cluster launch, two cluster barriers) is higher (9.4 vs 4.3 us), so at the
-// hot-path shapes (K = 1024 / 4096) the single-CTA kernel wins or ties. cg_set_tf32_pair(1) selects it.
-int g_pair_enabled = 0;
+// On by default (cg_set_tf32_pair(0) selects the single-CTA kernel for every shape). A dense GEMM on this 1 kW part runs
+// against the power cap, so what decides the sustained rate is energy per flop: the pair kernel fills 32 KB of shared
+// memory per SM and k-block instead of 48 KB and reads 64 instead of 96 B/clk of operands, and with both kernels held
+// at ~990 W for 1.5 s it sustains 639 / 640 / 613 TFLOP/s on the three 8192-row products against 560 / 563 / 581 for
+// the single-CTA kernel (cuBLAS TF32: 664 / 661 / 639), 574 / 574 / 541 against 542 / 554 / 510 at 1024 rows (cuBLAS:
+// 580 / 576 / 560) — tools/gemm_vs_cublas.py, profiles/r02c_gemm_vs_cublas_pair{0,1}.jsonl. Round 1 compared best-of-N
+// bursts, where the clocks have not yet come down and the two kernels tie.
+int g_pair_enabled = 1;
 bool pair_kernel_enabled() { return g_pair_enabled != 0; }
 
 bool pair_eligible(int m, int n, int k) { return pair_kernel_enabled() && m % 256 == 0 && n % 64 == 0 && k % BK == 0; }

@@ -110,7 +110,7 @@ void cg_set_graph_streams(int n);     /* side streams of the per-iteration CUDA 
 void cg_set_ew_jit_min(long long min_elems);
 int cg_ew_jit_available(void);
 long long cg_ew_jit_selftest(void);   /* compiles a program using every opcode; cubin bytes or -1 (no GPU needed) */
-void cg_set_tf32_pair(int on);        /* 1: 2-SM (cta_group::2) TF32 product kernel where the shape allows; default 0 */
+void cg_set_tf32_pair(int on);        /* 1 (default): 2-SM (cta_group::2) TF32 product kernel where the shape allows (m % 256 == 0); 0: single-CTA kernel */
 void cg_set_io_graph(int on);         /* 0: never put host transfers inside the iteration graph */
 /* dag mode. 1 (default): backward work that does not depend on the loss (Q3: a Sigmoid / Tanh hands its child the local
  * derivative only, src/optimize.rs:168-179 — every gate derivative, weight-gradient product and weight update of the

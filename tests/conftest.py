@@ -38,7 +38,7 @@ def cg():
     api.set_strict_gemm_max(64)
     api.set_ew_jit_min(32768)
     api.set_io_graph(True)
-    api.set_tf32_pair(False)
+    api.set_tf32_pair(True)
     api.set_hoist(True)
     api.set_vm_max_dim(48)
     api.set_tape_jit(True)

@@ -82,7 +82,7 @@ def c4_runs():
     api.set_fix_act_grad(False)
     api.set_fuse(True)
     api.set_cuda_graph(True)
-    api.set_tf32_pair(False)
+    api.set_tf32_pair(True)
     api.set_ew_jit_min(32768)
     api.set_io_graph(True)
     try:

@@ -398,7 +398,7 @@ def test_lstm_tf32_tensor_core_path(cg, oracle, pair):
             assert rel_err(lg[k], lo[k]) < 1e-3, k
     finally:
         oracle.set_mode("exact")
-        cg.set_tf32_pair(False)
+        cg.set_tf32_pair(True)
 
 
 def test_host_transfers_inside_the_iteration_graph(cg, oracle):

@@ -173,4 +173,4 @@ def test_gemm_tcgen05_tf32(cg, abis, dims, t1, t2, pair):
                 p.free(x)
     finally:
         cg.set_tf32(False)
-        cg.set_tf32_pair(False)
+        cg.set_tf32_pair(True)

@@ -15,3 +15,4 @@ import json
 d=json.loads(open("gpurun_out/r02c_bench_c4_f32.json").read().strip().splitlines()[-1])
 print("c4 f32: value", d["value"], "roofline", d["roofline"]["achieved"], d["roofline"]["peak"], d["roofline"]["frac"], d["clocks"])
 PY
+timeout 300 python tools/h2d_probe.py 8192 33 > gpurun_out/r02c_h2d_probe.json 2> gpurun_out/r02c_h2d_probe.err; echo "h2d rc=$?"; cat gpurun_out/r02c_h2d_probe.json

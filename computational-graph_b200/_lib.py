@@ -51,7 +51,7 @@ class ProductApi(Api):
 
     def __init__(self, lib: C.CDLL):
         super().__init__(lib, "cg_")
-        for name in ("set_tf32", "set_fix_act_grad", "set_fix_broadcast_sum", "set_fix_sub_sign", "set_fuse", "set_cuda_graph", "set_strict_gemm_max",
+        for name in ("set_tf32", "set_fix_act_grad", "set_fix_broadcast_sum", "set_fix_sub_sign", "set_fix_tied_params", "set_fuse", "set_cuda_graph", "set_strict_gemm_max",
                      "set_graph_streams", "set_io_graph", "set_tf32_pair", "set_hoist", "set_vm_max_dim", "set_tape_jit", "set_elide_root"):
             fn = self._sym(name)
             fn.restype, fn.argtypes = None, [C.c_int]
@@ -121,6 +121,7 @@ class ProductApi(Api):
     def set_fix_act_grad(self, on: bool): self.lib.cg_set_fix_act_grad(int(on))
     def set_fix_broadcast_sum(self, on: bool): self.lib.cg_set_fix_broadcast_sum(int(on))
     def set_fix_sub_sign(self, on: bool): self.lib.cg_set_fix_sub_sign(int(on))
+    def set_fix_tied_params(self, on: bool): self.lib.cg_set_fix_tied_params(int(on))
     def set_fuse(self, on: bool): self.lib.cg_set_fuse(int(on))
     def set_cuda_graph(self, on: bool): self.lib.cg_set_cuda_graph(int(on))
     def set_strict_gemm_max(self, dim: int): self.lib.cg_set_strict_gemm_max(int(dim))

@@ -201,6 +201,13 @@ void cg_set_fix_broadcast_sum(int v) {
     rt.fix_broadcast_sum = v;
   });
 }
+void cg_set_fix_tied_params(int v) {
+  guard_rc([&] {
+    Runtime& rt = Runtime::get();
+    if (rt.fix_tied_params != v) rt.dp_epoch++;  // the backward tape changes: invalidate cached plans
+    rt.fix_tied_params = v;
+  });
+}
 void cg_set_fix_sub_sign(int v) { guard_rc([&] { Runtime::get().fix_sub_sign = v; }); }  // construction-time rule
 // (these three choices are baked into a compiled plan — its captured graphs, its kernel choice and its resident-executor
 // eligibility — so a change invalidates the cached plans, like every other setter below)

@@ -7,8 +7,11 @@
 //   * gemm_strict_kernel — one thread per output element, k ascending, separate multiply and add
 //     roundings: bit-identical to the reference's naive triple loop. Used for small products where
 //     the latency of the launch dominates anyway (README LSTM, d <= 64).
-//   * gemm_tiled_kernel  — 128x128x16 shared-memory tiles, 8x8 register micro-tiles, double-buffered,
-//     FMA accumulation (k ascending per output element). FMA-pipe bound.
+//   * gemm_tiled_kernel  — 128x128x8 shared-memory tiles, 8x8 register micro-tiles, double-buffered,
+//     FMA accumulation (k ascending per output element). FMA-pipe bound. The micro-tile is accumulated with the
+//     packed FFMA2 of sm_100 (`__ffma2_rn`: two IEEE fma.rn per instruction, the A element broadcast from a scalar
+//     register): 32 FFMA2 + 4 LDS.128 per k instead of 64 FFMA + 4 LDS.128, so the issue slots no longer cap the FMA
+//     pipe (ncu, scalar version: issue active 77 %, 85 % of the issued instructions FFMA => pipe 66 % busy).
 // The tensor-core TF32 path lives in gemm_tcgen05.cu.
 #include "cg_common.h"
 
@@ -40,7 +43,7 @@ __global__ void __launch_bounds__(256) gemm_strict_kernel(const float* __restric
   *c = epilogue_apply(epi, acc, epi.mode != 0 ? *c : 0.0f);
 }
 
-constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+constexpr int BM = 128, BN = 128, BK = 8, PAD = 4;  // BK = 8: one float4 per thread and operand in flight (FFMA2 wants its registers in pairs)
 
 // Loads a (BK x TILE) operand tile into registers: element (kk, x) of the tile is op(M)(x0 + x, k0 + kk)
 // for A (x = row of C) or op(M)(k0 + kk, x0 + x) for B (x = column of C).
@@ -48,11 +51,10 @@ constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
 //   otherwise : contiguous along k.
 template <bool MN_CONTIG>
 __device__ __forceinline__ void load_tile(const float* __restrict__ M, int ld, int x0, int k0, int xmax, int kmax,
-                                          bool fast, float (&reg)[8]) {
+                                          bool fast, float (&reg)[4]) {
   const int t = threadIdx.x;
-#pragma unroll
-  for (int s = 0; s < 2; s++) {
-    const int f = t + s * 256;
+  {
+    const int s = 0, f = t;
     if (MN_CONTIG) {
       const int kk = f >> 5, x4 = (f & 31) * 4;
       const float* p = M + (size_t)(k0 + kk) * ld + x0 + x4;
@@ -64,7 +66,7 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ M, int ld, i
         for (int c = 0; c < 4; c++) reg[s * 4 + c] = (k0 + kk < kmax && x0 + x4 + c < xmax) ? p[c] : 0.0f;
       }
     } else {
-      const int x = f >> 2, k4 = (f & 3) * 4;
+      const int x = f >> 1, k4 = (f & 1) * 4;
       const float* p = M + (size_t)(x0 + x) * ld + k0 + k4;
       if (fast) {
         float4 v = *reinterpret_cast<const float4*>(p);
@@ -78,16 +80,15 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ M, int ld, i
 }
 
 template <bool MN_CONTIG>
-__device__ __forceinline__ void store_tile(float (*S)[BM + PAD], const float (&reg)[8]) {
+__device__ __forceinline__ void store_tile(float (*S)[BM + PAD], const float (&reg)[4]) {
   const int t = threadIdx.x;
-#pragma unroll
-  for (int s = 0; s < 2; s++) {
-    const int f = t + s * 256;
+  {
+    const int s = 0, f = t;
     if (MN_CONTIG) {
       const int kk = f >> 5, x4 = (f & 31) * 4;
       *reinterpret_cast<float4*>(&S[kk][x4]) = make_float4(reg[s * 4], reg[s * 4 + 1], reg[s * 4 + 2], reg[s * 4 + 3]);
     } else {
-      const int x = f >> 2, k4 = (f & 3) * 4;
+      const int x = f >> 1, k4 = (f & 1) * 4;
 #pragma unroll
       for (int c = 0; c < 4; c++) S[k4 + c][x] = reg[s * 4 + c];
     }
@@ -110,13 +111,13 @@ __global__ void __launch_bounds__(256, 2) gemm_tiled_kernel(const float* __restr
   const bool b_al = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 4 == 0);
   const bool m_full = m0 + BM <= m, n_full = n0 + BN <= n;
 
-  float acc[8][8];
+  float2 acc[8][4];  // acc[i][j2] = outputs (row i, columns 2 j2 and 2 j2 + 1) of the 8 x 8 micro-tile
 #pragma unroll
   for (int i = 0; i < 8; i++)
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+    for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.0f, 0.0f);
 
-  float ra[8], rb[8];
+  float ra[4], rb[4];
   const int ktiles = (k + BK - 1) / BK;
   {
     const bool kf = BK <= k;
@@ -137,17 +138,18 @@ __global__ void __launch_bounds__(256, 2) gemm_tiled_kernel(const float* __restr
     }
 #pragma unroll
     for (int kk = 0; kk < BK; kk++) {
-      float a[8], b[8];
       const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][kk][ri * 4]);
       const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][kk][64 + ri * 4]);
       const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][kk][cj * 4]);
       const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][kk][64 + cj * 4]);
-      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float2 b[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+      for (int i = 0; i < 8; i++) {
+        const float2 aa = make_float2(a[i], a[i]);  // FFMA2 takes the scalar register as a broadcast operand: no move
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; j++) acc[i][j] = __ffma2_rn(aa, b[j], acc[i][j]);
+      }
     }
     if (kt + 1 < ktiles) {
       store_tile<!TA>(As[cur ^ 1], ra);
@@ -167,20 +169,25 @@ __global__ void __launch_bounds__(256, 2) gemm_tiled_kernel(const float* __restr
       for (int ih = 0; ih < 2; ih++) {
         const int i = m0 + ih * 64 + ri * 4;
         float* c = C + (size_t)j * ldc + i;
-        const float* v = &acc[ih * 4][jh * 4 + jj];  // acc[ih*4 + ii][jh*4 + jj], stride 8
+        float v[4];  // rows ih*4 .. ih*4+3 of micro-tile column jh*4 + jj
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++) {
+          const float2 pr = acc[ih * 4 + ii][(jh * 4 + jj) >> 1];
+          v[ii] = ((jh * 4 + jj) & 1) ? pr.y : pr.x;
+        }
         if (c_al && i + 4 <= m) {
           float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
           if (epi.mode != 0) o = *reinterpret_cast<const float4*>(c);
           float4 w;
           w.x = epilogue_apply(epi, v[0], o.x);
-          w.y = epilogue_apply(epi, v[8], o.y);
-          w.z = epilogue_apply(epi, v[16], o.z);
-          w.w = epilogue_apply(epi, v[24], o.w);
+          w.y = epilogue_apply(epi, v[1], o.y);
+          w.z = epilogue_apply(epi, v[2], o.z);
+          w.w = epilogue_apply(epi, v[3], o.w);
           *reinterpret_cast<float4*>(c) = w;
         } else {
 #pragma unroll
           for (int ii = 0; ii < 4; ii++)
-            if (i + ii < m) c[ii] = epilogue_apply(epi, v[ii * 8], epi.mode != 0 ? c[ii] : 0.0f);
+            if (i + ii < m) c[ii] = epilogue_apply(epi, v[ii], epi.mode != 0 ? c[ii] : 0.0f);
         }
       }
     }

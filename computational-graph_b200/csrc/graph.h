@@ -87,6 +87,7 @@ struct Runtime {
   int fix_act_grad = 0;  // 0 = reproduce Q3
   int fix_broadcast_sum = 0;  // 0 = reproduce Q5 in the backward pass (scalar <- matrix error = mean); 1: sum
   int fix_sub_sign = 0;       // 0 = reproduce Q4's `0 - x -> x`; 1: `0 - x -> -x`
+  int fix_tied_params = 0;    // 0 = reproduce Q1 (every use site of a param drifts on its own); 1: one parameter per name
   int fuse = 1;          // 0 = one kernel per IR instruction (debug / ablation)
   int use_graph = 1;     // capture each iteration as a CUDA graph
   int graph_streams = 4; // side streams used when an iteration is captured as a DAG (0 = single stream)

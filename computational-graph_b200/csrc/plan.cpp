@@ -77,6 +77,16 @@ struct Builder {
   bool dp = false;
   bool in_backward = false;      // set around the backward walk: only there does fix_broadcast_sum apply
   int fix_broadcast_sum = 0;
+  // Corrected semantics (cg_set_fix_tied_params): every use of a parameter NAME is one parameter. The
+  // per-use-site copies stay (Q1's storage), but the backward walk only accumulates what each copy receives into one
+  // gradient per name — so every forward value it reads is the un-updated one — and after the walk every copy of the
+  // name takes the same update, p -= lr * (sum of contributions): the copies stay bit-identical.
+  int fix_tied_params = 0;
+  struct Tie {
+    int grad = -1;
+    std::vector<Function*> leaves;
+  };
+  std::vector<std::pair<std::string, Tie>> ties;  // in first-contribution order (deterministic tape)
 
   Builder(Plan& plan, float lr_, int fix) : p(plan), lr(lr_), fix_act_grad(fix), dp(dp_enabled()) {}
 
@@ -250,6 +260,19 @@ struct Builder {
 
   // ---- Param arm of backprop, optimize.rs:149-152 ----------------------------------------------------------------
   void sgd_leaf(Function& f, int error) {
+    if (fix_tied_params) {
+      Tie* t = nullptr;
+      for (auto& kv : ties)
+        if (kv.first == f.body->name) t = &kv.second;
+      if (!t) {
+        ties.emplace_back(f.body->name, Tie{});
+        t = &ties.back().second;
+      }
+      if (std::find(t->leaves.begin(), t->leaves.end(), &f) == t->leaves.end()) t->leaves.push_back(&f);
+      const int part = absorb(shape_of(f), error);  // in the parameter's shape (S <- M: mean, or sum when that is fixed too)
+      t->grad = t->grad < 0 ? part : emit(IOp::Add, sh(t->grad), t->grad, part);
+      return;
+    }
     int e2 = mul_imm(error, lr);                  // *error *= Constant::Scalar(learn_rate)
     int cur = leaf_val(f);
     int nv = new_fixed(sh(cur), f.value.buf);     // next version lives in the same leaf buffer
@@ -317,6 +340,21 @@ struct Builder {
         }
         break;
       default: break;
+    }
+  }
+
+  // fix_tied_params: the one update per name, applied to every copy, after the walk
+  void apply_tied_updates() {
+    for (auto& kv : ties) {
+      Tie& t = kv.second;
+      if (t.grad < 0) continue;
+      const int e2 = mul_imm(t.grad, lr);
+      for (Function* f : t.leaves) {
+        const int cur = leaf_val(*f);
+        const int nv = new_fixed(sh(cur), f->value.buf);
+        op_assign(B_SUB, cur, e2, nv);
+        leaf_cur[f] = nv;
+      }
     }
   }
 
@@ -1052,6 +1090,7 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root, bool 
   if (p.mode == 1 && !forward_only && dp_multimem_active() && migrate_dp_weights(root)) root.eval_plan.reset();
   Builder b(p, lr, rt.fix_act_grad);
   b.fix_broadcast_sum = rt.fix_broadcast_sum;
+  b.fix_tied_params = rt.fix_tied_params;
   b.forward(root);
   const Shape rsh = Builder::shape_of(root);
   p.root_n = rsh.n();
@@ -1081,6 +1120,7 @@ std::shared_ptr<Plan> build_plan(Function& root, float lr, bool keep_root, bool 
     b.in_backward = true;
     if (p.mode == 0) b.backprop_tree(root, error);
     else b.backprop_dag(root, error);
+    if (b.fix_tied_params) b.apply_tied_updates();
   }
 
   p.stats.tape_instrs = p.tape.size();

@@ -101,6 +101,10 @@ void cg_set_fix_act_grad(int on);     /* 1: sigmoid/tanh pass error*derivative (
  *   mean (Q5: src/ops.rs:79-80,103-104,126-134); sub_sign: `0 - x` builds `-x` instead of `x` (Q4: src/ops.rs:255-263). */
 void cg_set_fix_broadcast_sum(int on);
 void cg_set_fix_sub_sign(int on);
+/* tied_params: every use of a parameter NAME is one parameter (the reference gives each use site a private copy that
+ * drifts apart, Q1: src/function.rs:10-16). The backward pass accumulates one gradient per name from un-updated values
+ * and every copy takes the same update — true gradient descent on shared weights (an LSTM whose steps share W). */
+void cg_set_fix_tied_params(int on);
 void cg_set_fuse(int on);             /* 0: one kernel per tape instruction (ablation) */
 void cg_set_cuda_graph(int on);       /* 0: launch kernels eagerly instead of replaying a CUDA graph */
 void cg_set_strict_gemm_max(int dim); /* products with max(m,n,k) <= dim use the bit-exact kernel */

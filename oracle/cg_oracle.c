@@ -325,8 +325,13 @@ static void c_free(Constant *c) {
  *     the loss (root error == ones, i.e. the sum of the root's elements) with respect to a broadcast scalar — instead
  *     of the mean the reference's S<-M rule gives it (Q5; ops.rs:79-80,103-104,126-134). The forward pass keeps the mean:
  *     there it is the value-shape rule, not a gradient.
- *   FIX_SUB_SIGN: `0 - x` is `-x`; the reference shares Add's identity rule and returns `x` (Q4; ops.rs:255-263). */
-static int FIX_BROADCAST_SUM = 0, FIX_SUB_SIGN = 0, IN_BACKWARD = 0;
+ *   FIX_SUB_SIGN: `0 - x` is `-x`; the reference shares Add's identity rule and returns `x` (Q4; ops.rs:255-263).
+ *   FIX_TIED_PARAMS: every use of a parameter NAME is the same parameter. The reference gives each use site a private
+ *     copy that drifts apart (Q1; function.rs:10-16). Here the copies stay, but the backward walk only ACCUMULATES the
+ *     error each copy receives (reduced to the parameter's shape) into one gradient per name — every forward value it
+ *     reads is therefore the un-updated one — and after the walk every copy of the name takes the same update
+ *     p -= lr * (sum of the contributions), so the copies remain bit-identical: one parameter, true gradient descent. */
+static int FIX_BROADCAST_SUM = 0, FIX_SUB_SIGN = 0, IN_BACKWARD = 0, FIX_TIED_PARAMS = 0;
 static float m_avg(const Matrix *m) { /* ops.rs:438-442 */
   if (FIX_BROADCAST_SUM && IN_BACKWARD) return OPS.reduce_sum(m);
   return OPS.reduce_sum(m) / (float)((size_t)m->height * m->width);
@@ -457,6 +462,7 @@ void orc_set_mode(int m) { MODE = m; }
 void orc_set_fix_act_grad(int v) { FIX_ACT_GRAD = v; }
 void orc_set_fix_broadcast_sum(int v) { FIX_BROADCAST_SUM = v; }
 void orc_set_fix_sub_sign(int v) { FIX_SUB_SIGN = v; }
+void orc_set_fix_tied_params(int v) { FIX_TIED_PARAMS = v; }
 long orc_count_gemm(void) { return COUNT_GEMM; }
 void orc_reset_counts(void) { COUNT_GEMM = COUNT_OPS = 0; }
 
@@ -714,8 +720,71 @@ static void forward(Function *f, int nargs, const char **names, const Constant *
   forward_tree(f, nargs, names, args);
 }
 
+/* FIX_TIED_PARAMS: one accumulated gradient per parameter name, and the leaves (use sites) that carry that name */
+typedef struct {
+  char name[64];
+  Constant grad;
+  int has_grad;
+  Function **leaves;
+  int n, cap;
+} TieGroup;
+static TieGroup *TIES = NULL;
+static int N_TIES = 0, CAP_TIES = 0;
+static TieGroup *tie_group(const char *name) {
+  for (int i = 0; i < N_TIES; i++)
+    if (strcmp(TIES[i].name, name) == 0) return &TIES[i];
+  if (N_TIES == CAP_TIES) {
+    CAP_TIES = CAP_TIES ? CAP_TIES * 2 : 16;
+    TIES = (TieGroup *)realloc(TIES, (size_t)CAP_TIES * sizeof(TieGroup));
+  }
+  TieGroup *g = &TIES[N_TIES++];
+  memset(g, 0, sizeof *g);
+  snprintf(g->name, sizeof g->name, "%s", name);
+  return g;
+}
+static void tie_accumulate(Function *f, const Constant *error) {
+  TieGroup *g = tie_group(f->body->name);
+  int seen = 0;
+  for (int i = 0; i < g->n; i++) seen |= g->leaves[i] == f;
+  if (!seen) {
+    if (g->n == g->cap) {
+      g->cap = g->cap ? g->cap * 2 : 8;
+      g->leaves = (Function **)realloc(g->leaves, (size_t)g->cap * sizeof(Function *));
+    }
+    g->leaves[g->n++] = f;
+  }
+  Constant part = c_empty_like(&f->value); /* the contribution in the parameter's shape (S<-M: mean, or sum when fixed) */
+  c_absorb(&part, error);
+  if (!g->has_grad) {
+    g->grad = part;
+    g->has_grad = 1;
+  } else {
+    c_op_assign(B_ADD, &g->grad, &part);
+    c_free(&part);
+  }
+}
+static void tie_apply(float lr) {
+  Constant clr = c_scalar(lr);
+  for (int i = 0; i < N_TIES; i++) {
+    TieGroup *g = &TIES[i];
+    if (g->has_grad) {
+      c_op_assign(B_MUL, &g->grad, &clr);
+      for (int k = 0; k < g->n; k++) c_op_assign(B_SUB, &g->leaves[k]->value, &g->grad);
+      c_free(&g->grad);
+    }
+    free(g->leaves);
+  }
+  free(TIES);
+  TIES = NULL;
+  N_TIES = CAP_TIES = 0;
+}
+
 /* Param arm of backprop, optimize.rs:149-152 */
 static void sgd_leaf(Function *f, Constant *error, float lr) {
+  if (FIX_TIED_PARAMS) {
+    tie_accumulate(f, error);
+    return;
+  }
   Constant clr = c_scalar(lr);
   c_op_assign(B_MUL, error, &clr);      /* *error *= Scalar(lr)   (possibly matrix * scalar) */
   c_op_assign(B_SUB, &f->value, error); /* value -= error         (possibly scalar -= matrix) */
@@ -912,6 +981,7 @@ static int run_minimize(Function *f, int nargs, const char **names, const Consta
     } else {
       c_free(&error);
     }
+    if (FIX_TIED_PARAMS) tie_apply(lr);
     IN_BACKWARD = 0;
   }
   free(order.v);

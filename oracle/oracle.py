@@ -40,6 +40,7 @@ class OracleApi(Api):
         lib.orc_set_fix_act_grad.argtypes = [ctypes.c_int]
         lib.orc_set_fix_broadcast_sum.argtypes = [ctypes.c_int]
         lib.orc_set_fix_sub_sign.argtypes = [ctypes.c_int]
+        lib.orc_set_fix_tied_params.argtypes = [ctypes.c_int]
 
     def use_ref(self, which: str = "O0") -> bool:
         """Route every matrix op through the reference-compiled CPU backend. Returns False when

@@ -33,6 +33,9 @@ def cg():
     api.set_mode("exact")
     api.set_tf32(False)
     api.set_fix_act_grad(False)
+    api.set_fix_broadcast_sum(False)
+    api.set_fix_sub_sign(False)
+    api.set_fix_tied_params(False)
     api.set_fuse(True)
     api.set_cuda_graph(True)
     api.set_strict_gemm_max(64)

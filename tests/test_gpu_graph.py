@@ -7,7 +7,7 @@ glibc's by <= 2 ulp. TF32 runs use 1e-3 and say so.
 import numpy as np
 import pytest
 
-from helpers import c2_graph, leaves_dict, readme_lstm, rel_err
+from helpers import c2_graph, close_err, leaves_dict, readme_lstm, rel_err
 from reference_cases import CASES, run_case
 
 pytestmark = pytest.mark.gpu
@@ -597,3 +597,43 @@ def test_corrected_broadcast_sum_and_sub_sign_match_the_oracle(cg, oracle):
             assert np.allclose(np.asarray(f.leaves()[0][1]), want)
         finally:
             cg.set_fix_sub_sign(False)
+
+
+@pytest.mark.parametrize("mode", ["exact", "dag"])
+def test_tied_parameters_match_the_oracle(cg, oracle, mode):
+    """cg_set_fix_tied_params on the CUDA path against the oracle (checked against finite differences in the CPU tier):
+    the reference's complex_test graph with both uses of x tied (bit-exact: no transcendental), and an LSTM whose time
+    steps share their weights — trajectory and leaves within 1e-5, copies of one name bit-identical."""
+    B = np.array([[1.0, 2.0], [3.0, 4.0]], dtype=np.float32)
+
+    def build(api):
+        x = api.Function.scalar_param("x", 0.5)
+        return ((x - api.Function.scalar(2.0)) * (x + api.Function.constant(api.Constant(B))) - api.Function.scalar(10.0)).sq()
+
+    cg.set_mode(mode)
+    oracle.set_mode(mode)
+    cg.set_fix_tied_params(True)
+    oracle.lib.orc_set_fix_tied_params(1)
+    try:
+        fg, fo = build(cg), build(oracle)
+        tg = np.asarray(fg.minimize({}, 1e-4, 6, trace=True))
+        to = np.asarray(fo.minimize({}, 1e-4, 6, trace=True))
+        assert np.array_equal(tg.view(np.int32), to.view(np.int32))
+        lg, lo = fg.leaves(), fo.leaves()
+        assert [np.float32(v) for _, v in lg] == [np.float32(v) for _, v in lo] and lg[0][1] == lg[1][1]
+        fg, fo = readme_lstm(cg, 12, T=3, seed=5), readme_lstm(oracle, 12, T=3, seed=5)
+        tg = fg.minimize({}, 1e-3, 5, trace=True)
+        to = fo.minimize({}, 1e-3, 5, trace=True)
+        assert close_err(tg, to, 1e-5) <= 1.0
+        by_name = {}
+        for (n, vg), (no, vo) in zip(fg.leaves(), fo.leaves()):
+            assert n == no and close_err(vg, vo, 1e-5) <= 1.0, n
+            by_name.setdefault(n, []).append(np.asarray(vg))
+        assert len(by_name["Wi"]) == 3
+        for n, copies in by_name.items():
+            for c in copies[1:]:
+                assert np.array_equal(c.view(np.int32), copies[0].view(np.int32)), n
+    finally:
+        cg.set_fix_tied_params(False)
+        oracle.lib.orc_set_fix_tied_params(0)
+        oracle.set_mode("exact")

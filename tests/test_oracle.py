@@ -371,3 +371,45 @@ def test_corrected_broadcast_sum_and_sub_sign_match_finite_differences(oracle):
             oracle.lib.orc_set_fix_sub_sign(0)
     assert np.allclose(step(0), 0.4)   # reference: 0 - m IS m, so m descends
     assert np.allclose(step(1), 0.6)   # corrected: d(sum(-m))/dm = -1, so m ascends
+
+
+def test_tied_parameters_match_finite_differences(oracle):
+    """SURVEY §8f-2, tied parameters: with fix_tied_params every use of a parameter NAME is one parameter — the backward
+    walk accumulates one gradient per name from un-updated values and every copy takes the same update. On the
+    reference's own `complex_test` graph ((x-2)*(x+B)-10)^2 (src/main.rs:144-154), where x is used twice, the update then
+    equals -lr * dL/dx of L = sum of the root's elements (with the broadcast sum fixed too), in exact AND dag mode, and
+    both copies of x stay identical; without the switch the two copies drift apart (Q1)."""
+    F, Cn = oracle.Function, oracle.Constant
+    B = np.array([[1.0, 2.0], [3.0, 4.0]], dtype=np.float32)
+    lr = 1e-4
+
+    def build(x0):
+        x = F.scalar_param("x", x0)
+        return ((x - F.scalar(2.0)) * (x + F.constant(Cn(B))) - F.scalar(10.0)).sq()
+
+    def loss(x0):
+        return float(np.sum(np.asarray(build(x0).minimize({}, lr, 1, trace=True), dtype=np.float64)))
+
+    x0, h = 0.5, 1e-3
+    fd = (loss(x0 + h) - loss(x0 - h)) / (2 * h)
+    for mode in ("exact", "dag"):
+        oracle.set_mode(mode)
+        oracle.lib.orc_set_fix_tied_params(1)
+        oracle.lib.orc_set_fix_broadcast_sum(1)
+        try:
+            f = build(x0)
+            f.minimize({}, lr, 1)
+            leaves = [float(v) for _, v in f.leaves()]
+            assert len(leaves) == 2 and leaves[0] == leaves[1]
+            assert abs((x0 - leaves[0]) / lr - fd) <= 2e-3 * abs(fd), (mode, (x0 - leaves[0]) / lr, fd)
+            f.minimize({}, lr, 3)
+            leaves = [float(v) for _, v in f.leaves()]
+            assert leaves[0] == leaves[1]
+        finally:
+            oracle.lib.orc_set_fix_tied_params(0)
+            oracle.lib.orc_set_fix_broadcast_sum(0)
+            oracle.set_mode("exact")
+    f = build(x0)
+    f.minimize({}, lr, 3)
+    leaves = [float(v) for _, v in f.leaves()]
+    assert leaves[0] != leaves[1]  # the reference: two private copies (Q1)

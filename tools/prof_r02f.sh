@@ -1,0 +1,5 @@
+# round 2, 1 GPU: does the number of hardware work queues decide how well the H2D copies of an end-to-end call overlap the iteration?
+mkdir -p gpurun_out
+for c in 32 2; do
+  CUDA_DEVICE_MAX_CONNECTIONS=$c timeout 600 python tools/e2e_probe2.py 32 8192 > gpurun_out/r02f_e2e_probe_T32_conn$c.json 2> gpurun_out/r02f_e2e_probe_conn$c.err; echo "conn=$c rc=$?"; cat gpurun_out/r02f_e2e_probe_T32_conn$c.json
+done

@@ -38,6 +38,10 @@ import time
 
 import numpy as np
 
+# before torch creates the CUDA context: enough hardware work queues that the input copies of an end-to-end call do not
+# wait behind kernels of the iteration graph (computational-graph_b200/csrc/graph.cpp)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

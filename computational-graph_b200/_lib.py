@@ -2,6 +2,11 @@
 from __future__ import annotations
 
 import ctypes as C
+import os as _os
+
+# more hardware work queues, so that the H2D copies of an end-to-end call do not queue behind kernels of the iteration graph
+# (csrc/graph.cpp says why); must be set before the CUDA context exists
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import os
 import weakref
 from typing import Dict, List, Optional

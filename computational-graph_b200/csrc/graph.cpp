@@ -63,6 +63,17 @@ BufRef DevBuf::alloc(size_t n) {
   return b;
 }
 
+// An end-to-end `minimize(&args, lr, 1)` call copies its inputs on a stream of its own while the iteration graph runs.
+// The graph's branches and that stream are mapped onto the device's hardware work queues — 8 by default — and a copy that
+// lands in a queue behind kernels of the graph waits for them: at config 5 (33 inputs, 4.4 GB) the call took 293 ms
+// against 250 ms for the iteration itself, 307 ms with 2 queues and 257 ms with 32 (profiles/r02f_e2e_probe_T32_conn*.json).
+// So the library asks for 32 queues unless the host has chosen; this must happen before the CUDA context exists, hence
+// a load-time initialiser (the Python host layer and bench.py set the same default before importing torch).
+static const int g_connections_default = [] {
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", /*overwrite=*/0);
+  return 0;
+}();
+
 static Runtime g_rt;
 Runtime& Runtime::get() {
   if (!g_rt.stream) g_rt.init();

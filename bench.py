@@ -17,7 +17,8 @@ when neither is available).
   parity     : N > 1 only, BEFORE anything is timed: the data-parallel run against the same kernels on one GPU and
                against the CPU oracle (f32 and TF32 shapes, every weight through the fused exchange); a failure ends
                the run with a non-zero exit code
-  secondary  : N = 1 only: BASELINE config 4 (TF32 and FP32 products) and configs 1-3, each timed the same way
+  secondary  : N = 1 only: BASELINE config 4 (TF32, FP32-accurate 3 x TF32 on the tensor core, and FP32 SIMT products) and
+               configs 1-3, each timed the same way
   same_config: N = 1 only: workloads the REFERENCE can run (README LSTM sweep, exact mode; a square LSTM in dag mode),
                GPU and reference CPU both measured in this run — no extrapolation
   peaks      : TF32 (cuBLAS through torch.matmul; best-of-10 bursts, and ours vs cuBLAS SUSTAINED at the power cap) and
@@ -195,7 +196,7 @@ def measure_lstm(api, torch, dist, wl: Workload, product: str, steps: int, warmu
     """Builds the workload's graph on this rank and measures it: device-resident, end to end, per-kernel."""
     world = wl.world
     api.set_mode("dag")
-    api.set_tf32(product == "tf32")
+    api.set_tf32({"f32": 0, "tf32": 1, "tf32x3": 2}[product])
     f, host_args = build_lstm(api, wl.rows, I, H, wl.T, wl.seed, with_inputs=True, shard=rank)
     pinned, keep = {}, []
     for k, v in host_args.items():
@@ -242,6 +243,12 @@ def measure_lstm(api, torch, dist, wl: Workload, product: str, steps: int, warmu
         peak = pk["bf16_sustained"] / 2.0
         peak_note = (f"1/2 x {pk['source']} sustained cuBLAS bf16 ({pk['bf16_sustained']} TFLOP/s): tcgen05 kind::tf32 issues "
                      "at half the kind::f16 rate; the TF32 cuBLAS rate measured in this run is under `peaks`")
+        bound = "tensor"
+    elif product == "tf32x3":
+        peak = pk["bf16_sustained"] / 6.0
+        peak_note = (f"1/6 x {pk['source']} sustained cuBLAS bf16 ({pk['bf16_sustained']} TFLOP/s): FP32-accurate products on the "
+                     "tensor core issue three tcgen05 kind::tf32 MMAs per k-step (operands split in shared memory into the part TF32 "
+                     "keeps and the part it drops), so the ceiling is a third of the TF32 rate; flops counted once (2 m n k)")
         bound = "tensor"
     else:
         nominal = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
@@ -405,6 +412,33 @@ def measure_peaks(torch, api, rows_list):
 # ---------------------------------------------------------------------------------------------------------
 # parity of the data-parallel path, checked inside the bench run (N > 1), before anything is timed
 # ---------------------------------------------------------------------------------------------------------
+def nccl_allreduce_reference(torch, dist, world, n_floats=I * H, reps=20):
+    """What the LIBRARY takes for the same exchange: `ncclAllReduce` (through torch.distributed) of one weight gradient
+    (4096 x 4096 f32, 64 MiB), back to back, no compute beside it — the figure the fused exchange kernel's serialised time
+    per weight (`kernel_share.exchange_ms_serialised` / kernels.exchange) stands against. The fused kernel also applies the
+    SGD update, which NCCL leaves to a further pass over the weight."""
+    g = torch.ones(n_floats, dtype=torch.float32, device="cuda")
+    for _ in range(5):
+        dist.all_reduce(g)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dist.all_reduce(g)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    nbytes = 4.0 * n_floats
+    del g
+    return {"what": "ncclAllReduce (torch.distributed, NCCL %s) of one 64 MiB weight gradient, %d back to back, max over ranks"
+                    % (".".join(str(x) for x in torch.cuda.nccl.version()), reps),
+            "us": ms * 1e3, "algbw_GBps": nbytes / (ms * 1e-3) / 1e9,
+            "busbw_GBps": nbytes / (ms * 1e-3) / 1e9 * 2.0 * (world - 1) / world}
+
+
 def dp_parity(api, pkg, torch, dist, rank, world, local_rank, multimem, tf32_batch=None, scale_lr=True):
     """The sharded run with every weight through the fused exchange, against (a) the same kernels on ONE GPU over the
     full batch and (b) the CPU oracle (dag mode). One f32 shape (1e-5) and one TF32 shape (1e-3; against the f32 oracle
@@ -692,7 +726,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--product", default=os.environ.get("CG_BENCH_PRODUCT", "tf32"), choices=["tf32", "f32"])
+    ap.add_argument("--product", default=os.environ.get("CG_BENCH_PRODUCT", "tf32"), choices=["tf32", "tf32x3", "f32"],
+                    help="tf32: tcgen05 TF32 products (1e-3); tf32x3: FP32-accurate products on the tensor core, 3 x TF32 split (1e-5); "
+                         "f32: FP32 SIMT products (1e-5)")
     ap.add_argument("--config", default=os.environ.get("CG_BENCH_CONFIG", "c5"), choices=["c4", "c5"],
                     help="c5 (default, every N): BASELINE config 5, T=32, global batch 8192, strong scaling; "
                          "c4: BASELINE config 4, 1024 rows per GPU, weak scaling")
@@ -749,6 +785,7 @@ def main():
     measured = {}
     if rank == 0 and world == 1:
         measured = measure_peaks(torch, api, sorted({wl.rows, 1024}))
+    nccl_ref = nccl_allreduce_reference(torch, dist, world) if world > 1 else None
 
     line = measure_lstm(api, torch, dist, wl, args.product, args.steps, args.warmup, rank, local_rank, measured)
     if world > 1:
@@ -756,6 +793,11 @@ def main():
         line["multimem_supported"] = api.dp_multimem_supported() or api.dp_multimem_reason()
         if parity is not None:
             line["parity"] = parity
+        n_ex = line["kernel_share"]["kernels"]["exchange"]
+        line["exchange_vs_nccl"] = {
+            "ours_us_per_weight_serialised": line["kernel_share"]["exchange_ms_serialised"] * 1e3 / n_ex if n_ex else None,
+            "ours_includes": "sum over ranks + SGD update + new weight in every rank's memory (one kernel)",
+            "nccl": nccl_ref}
     if measured:
         line["peaks"] = measured
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -764,8 +806,8 @@ def main():
         sec = {}
         other = Workload("c4" if args.config == "c5" else "c5", 1)
         k = max(3, min(args.steps, 10))
-        for product in ("tf32", "f32"):
-            l2 = measure_lstm(api, torch, None, other, product, k if product == "tf32" else max(3, k // 2), 3, 0, local_rank, measured)
+        for product in ("tf32", "tf32x3", "f32"):
+            l2 = measure_lstm(api, torch, None, other, product, k if product != "f32" else max(3, k // 2), 3, 0, local_rank, measured)
             sec[f"{other.name}_{product}"] = {key: l2[key] for key in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "dtype",
                                                                    "config", "e2e", "gpu_launches", "roofline", "kernel_share", "clocks")}
         sec.update(secondary_small_configs(api))

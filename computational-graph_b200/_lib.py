@@ -122,7 +122,7 @@ class ProductApi(Api):
             from .api import GraphError
             raise GraphError(self._last_error().decode())
 
-    def set_tf32(self, on: bool): self.lib.cg_set_tf32(int(on))
+    def set_tf32(self, on): self.lib.cg_set_tf32(int(on))  # 0 FP32 SIMT, 1 TF32, 2 FP32-accurate 3xTF32
     def set_fix_act_grad(self, on: bool): self.lib.cg_set_fix_act_grad(int(on))
     def set_fix_broadcast_sum(self, on: bool): self.lib.cg_set_fix_broadcast_sum(int(on))
     def set_fix_sub_sign(self, on: bool): self.lib.cg_set_fix_sub_sign(int(on))

@@ -506,7 +506,7 @@ void gemm(const Matrix* m1, bool t1, const Matrix* m2, bool t2, Matrix* r) {
   if (w2 != r->width) die("width2 must equal result->width");
   LEGACY_TRY(Runtime& rt = Runtime::get();
              launch_gemm(m1->array, t1, m2->array, t2, r->array, (int)h1, (int)w2, (int)inner, (int)m1->height,
-                         (int)m2->height, (int)r->height, GemmEpilogue{}, rt.tf32 != 0, rt.stream);
+                         (int)m2->height, (int)r->height, GemmEpilogue{}, rt.tf32, rt.stream);
              rt.launches++;)
 }
 static bool legacy_cmp(bool less, const Matrix* m, float x) {

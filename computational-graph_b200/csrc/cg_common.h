@@ -131,11 +131,16 @@ void gemm_tf32_set_max_ctas(int n);  // persistent grid of the TF32 product (def
 void gemm_tf32_set_pair(int on);  // 1: CTA-pair (cta_group::2) kernel for shapes with m % 256 == 0 and n % 64 == 0
 void launch_gemm_tf32(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda,
                       int ldb, int ldc, const GemmEpilogue& epi, cudaStream_t stream);
+// FP32-accurate product on the tensor core: every operand split in shared memory into the part TF32 keeps and the part
+// it drops, three MMAs per k-step (CTA-pair kernel; m % 256 == 0).
+bool gemm_tf32x3_eligible(int m, int n, int k, bool ta, bool tb);
+void launch_gemm_tf32x3(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda,
+                        int ldb, int ldc, const GemmEpilogue& epi, cudaStream_t stream);
 
-// Shape-based dispatch: strict (max(m,n,k) <= Runtime::strict_gemm_max) | tcgen05 TF32 (allow_tf32 and
-// eligible) | tiled FP32 SIMT.
+// Shape-based dispatch: strict (max(m,n,k) <= Runtime::strict_gemm_max) | tcgen05 TF32 (precision 1 and eligible) |
+// tcgen05 3 x TF32 (precision 2 and eligible) | tiled FP32 SIMT.
 void launch_gemm(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda, int ldb,
-                 int ldc, const GemmEpilogue& epi, bool allow_tf32, cudaStream_t stream);
+                 int ldc, const GemmEpilogue& epi, int precision, cudaStream_t stream);
 
 // Data-parallel sum-allreduce of a weight gradient over NCCL (dp.cpp). In place.
 void dp_allreduce_sum(float* buf, size_t n, cudaStream_t stream);

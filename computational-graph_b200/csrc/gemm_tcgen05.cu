@@ -102,6 +102,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 shared memory descriptor"): start address, leading /
@@ -309,6 +318,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Arrival on a barrier of the peer CTA that publishes SHARED-memory writes to the tensor core (the splitters' lo tiles):
+// the writes were already made visible to the async proxy by fence.proxy.async, so the arrival needs no cluster-scope
+// release — `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR and cost the splitters half their time (ncu source
+// page, profiles/r02l_*). Same form as CUTLASS's ClusterBarrier::arrive(cta_id).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
@@ -339,8 +355,18 @@ __device__ __forceinline__ void tcgen05_mma_tf32_pair(uint32_t tmem_d, uint64_t 
       : "memory");
 }
 
+// What the tensor core drops when it truncates an f32 operand to TF32: exact, two instructions per element (the splitters
+// are issue-bound). An infinite operand gives lo = inf - inf = nan, so a product that plain f32 arithmetic would have
+// made inf comes out nan — non-finite either way.
+__device__ __forceinline__ float tf32_lo(float x) {
+  return __fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+}
+
 // The tile sequence of one pair (static round-robin over (row-block, column-tile)): every role of both CTAs walks
 // the same list. Consecutive pairs take consecutive column tiles of one row-block, so they share its A rows in L2.
+// (Tried and dropped, profiles/r02m_tile_order_prefetch.txt: taking the row-blocks in bands so that B streams past an
+// L2-resident A panel, and L2 prefetch of later k-blocks — DRAM reads fall, the rate does not move: the kernels run
+// against the power cap, not against operand latency.)
 struct ChunkWalk {
   int t, ntiles, stride, tiles_n, wmax;
   __device__ __forceinline__ ChunkWalk(int pair, int npairs, int total_cols, int n, int wmax_) : wmax(wmax_) {
@@ -360,11 +386,43 @@ struct ChunkWalk {
   }
 };
 
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// SPLIT3 — FP32-accurate products on the tensor core ("3xTF32"). The tensor core truncates every f32 operand to its top 10
+// mantissa bits (hi); the bits it drops, lo = x - hi, are themselves an f32 (exact). Six more warps per CTA (the
+// "splitters") compute lo for every staged tile, in shared memory, right behind the TMA: they wait on the CTA's own full
+// barrier, read the stage, write lo at the same (swizzled) position of a second tile behind it, make the writes visible to
+// the async proxy and arrive on the LEADER's split barrier, which is what the MMA thread waits on. Per k-step three MMAs:
+//   A_lo.B + A.B_lo  ->  the LO accumulator          A.B  ->  the HI accumulator
+//   = lo_a' hi_b + hi_a lo_b'                             = hi_a hi_b           (primes: lo truncated to ITS top 10 bits)
+// which leaves out lo_a lo_b (2^-22 of a term on average) and the second truncations (< 2^-21): a product term is good to
+// ~1e-6. Nothing is materialised in HBM and the operands cross L2 -> shared memory once; a stage holds four tiles.
+//
+// The tensor core's own accumulation is the other half of the problem: every tcgen05.mma adds its 8-deep partial sum to
+// the f32 accumulator with TRUNCATION, half an ulp of the accumulator lost towards zero per instruction — measured on this
+// part: k = 4096 through one accumulator ends 770 ulps short (1.5e-3 on a value of 30). So (a) the small terms have an
+// accumulator of their own, 2^-11 of the size, whose truncations do not matter, and (b) the contraction is cut into
+// chunks of SPLIT_KC k-blocks (256 deep: 32 truncating adds), each into a fresh accumulator stage, and the chunks are
+// summed by the epilogue warps in registers with round-to-nearest adds while the next chunk is on the tensor core. That
+// needs hi + lo for two stages in the 512 TMEM columns, hence column tiles of <= 128 here, and the running sum in
+// registers: eight epilogue warps, 64 sums per thread. Error of a k = 4096 product: ~16 ulps, what a k-ascending f32 FMA loop gives.
+//
+// Barriers in SPLIT3:                     full[s]   per CTA, its own producer's arrival + its own bytes
+//                                        split[s]  leader only, 12 arrivals (6 splitter warps x 2 CTAs)
+//                                        tfull[a] / tempty[a]  once per CHUNK instead of once per tile
+constexpr int SPLIT_KC = 8;
+constexpr int SPLIT_STAGES = 4;
+constexpr int SPLIT_EPI_WARPS = 8;    // warps 2-9: two per TMEM lane quad, 64 columns of the tile each (64 running sums per thread)
+constexpr int SPLIT_SPLIT_WARPS = 6;  // warps 10-15
+constexpr uint32_t SPLIT_TILE_BYTES = A_BYTES2 + 64 * BK * 4;  // 128 rows of A + this CTA's <= 64 columns of B: 24 KB
+constexpr int PAIR_THREADS = 192, PAIR_THREADS_SPLIT3 = 512;
+
+template <bool A_MN, bool B_MN, bool SPLIT3>
+__global__ void __launch_bounds__(SPLIT3 ? PAIR_THREADS_SPLIT3 : PAIR_THREADS, 1)
     gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_big,
                           const __grid_constant__ CUtensorMap map_b_small, float* __restrict__ C, int m, int n, int k, int ldc,
                           int epi_mode, float lr, int wmax) {
+  constexpr int NST = SPLIT3 ? SPLIT_STAGES : STAGES2;
+  constexpr uint32_t HB = SPLIT3 ? SPLIT_TILE_BYTES : STAGE_BYTES2;  // [A][B]: what the TMA stages
+  constexpr uint32_t SB = SPLIT3 ? 2 * HB : HB;                      // SPLIT3: [A][B][A_lo][B_lo]
   // B arrives in one box of wmax / 2 columns for a full-width chunk, in 16-row (K-major) / 32-column (MN-major) boxes for
   // the partial chunks at the ends of a range: TMA issue cost is per instruction, so the common case must be one box.
   constexpr int SMALL = B_MN ? 32 : 16;
@@ -372,11 +430,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   constexpr uint32_t TMEM_COLS = 512;  // 2 accumulator stages of <= 256 columns
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE_BYTES2);
-  uint64_t* empty_bar = full_bar + STAGES2;
-  uint64_t* tfull_bar = empty_bar + STAGES2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NST * SB);
+  uint64_t* empty_bar = full_bar + NST;
+  uint64_t* tfull_bar = empty_bar + NST;
   uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
+  uint64_t* split_bar = tempty_bar + ACC_STAGES;  // SPLIT3 only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split_bar + NST);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader
@@ -387,13 +446,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_big) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_small) : "memory");
-    for (int s = 0; s < STAGES2; s++) {
+    for (int s = 0; s < NST; s++) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 2 * SPLIT_SPLIT_WARPS);
     }
     for (int s = 0; s < ACC_STAGES; s++) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], SPLIT3 ? 2 * SPLIT_EPI_WARPS : 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -420,9 +480,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const uint32_t bytes = A_BYTES2 + (uint32_t)half * BK * 4;
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE_BYTES2;
+          uint8_t* sa = smem + stage * SB;
           uint8_t* sb = sa + A_BYTES2;
-          const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          // SPLIT3: the bytes are counted where they land (the CTA's splitters wait for them); otherwise on the leader
+          const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), SPLIT3 ? rank : 0);
           if (A_MN) tma2_load_3d(sa, &map_a, lbar, 0, kb * BK, m0 / 32);
           else tma2_load_2d(sa, &map_a, lbar, kb * BK, m0);
           int done = 0;
@@ -434,8 +495,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             for (; done < half; done += SMALL) tma2_load_2d(sb + done * 128, &map_b_small, lbar, kb * BK, b0 + done);
           }
           // the leader accounts for the bytes of both CTAs (its single arrival + 2 x bytes complete the phase)
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * bytes);
-          if (++stage == STAGES2) stage = 0, phase ^= 1;
+          if (SPLIT3) mbar_expect_tx(&full_bar[stage], bytes);
+          else if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * bytes);
+          if (++stage == NST) stage = 0, phase ^= 1;
         }
       }
     }
@@ -449,26 +511,138 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         // D = F32, A = B = TF32, major bits, N >> 3, M = 256 >> 4
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                ((uint32_t)(w >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // both epilogues have drained this accumulator stage
-        tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * 256;
-        for (int kb = 0; kb < num_kb; kb++) {
-          mbar_wait(&full_bar[stage], phase);  // both CTAs' bytes have landed
+        if (!SPLIT3) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // both epilogues have drained this accumulator stage
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES2), sb = sa + A_BYTES2;
+        }
+        for (int kb = 0; kb < num_kb; kb++) {
+          const bool chunk_start = SPLIT3 && kb % SPLIT_KC == 0;
+          if (chunk_start) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tcgen05_fence_after();
+          }
+          const uint32_t tmem_d = tmem_base + acc * 256;  // SPLIT3: hi accumulator; lo accumulator 128 columns behind
+          mbar_wait(SPLIT3 ? &split_bar[stage] : &full_bar[stage], phase);  // both CTAs' bytes have landed (and are split)
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * SB), sb = sa + A_BYTES2;
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; kk++) {
             const uint64_t da = A_MN ? make_smem_desc(sa + kk * MN_STEP, MN_LBO, MN_SBO, MN_LAYOUT)
                                      : make_smem_desc(sa + kk * K_STEP, K_LBO, K_SBO, 2);
             const uint64_t db = B_MN ? make_smem_desc(sb + kk * MN_STEP, MN_LBO, MN_SBO, MN_LAYOUT)
                                      : make_smem_desc(sb + kk * K_STEP, K_LBO, K_SBO, 2);
-            tcgen05_mma_tf32_pair(tmem_d, da, db, idesc, (kb | kk) != 0);
+            if (SPLIT3) {
+              const uint32_t la = sa + HB, lb = sb + HB;
+              const uint64_t da_lo = A_MN ? make_smem_desc(la + kk * MN_STEP, MN_LBO, MN_SBO, MN_LAYOUT)
+                                          : make_smem_desc(la + kk * K_STEP, K_LBO, K_SBO, 2);
+              const uint64_t db_lo = B_MN ? make_smem_desc(lb + kk * MN_STEP, MN_LBO, MN_SBO, MN_LAYOUT)
+                                          : make_smem_desc(lb + kk * K_STEP, K_LBO, K_SBO, 2);
+              const uint32_t fresh = (chunk_start && kk == 0) ? 0u : 1u;
+              tcgen05_mma_tf32_pair(tmem_d + 128, da_lo, db, idesc, fresh);
+              tcgen05_mma_tf32_pair(tmem_d + 128, da, db_lo, idesc, 1);
+              tcgen05_mma_tf32_pair(tmem_d, da, db, idesc, fresh);
+            } else {
+              tcgen05_mma_tf32_pair(tmem_d, da, db, idesc, (kb | kk) != 0);
+            }
           }
           tcgen05_commit_pair(&empty_bar[stage]);  // frees the slot in BOTH CTAs once these MMAs have read it
-          if (++stage == STAGES2) stage = 0, phase ^= 1;
+          if (++stage == NST) stage = 0, phase ^= 1;
+          if (SPLIT3 && (kb % SPLIT_KC == SPLIT_KC - 1 || kb == num_kb - 1)) {
+            tcgen05_commit_pair(&tfull_bar[acc]);  // this chunk's accumulators complete -> both epilogues
+            if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
+          }
         }
-        tcgen05_commit_pair(&tfull_bar[acc]);  // accumulators complete -> both epilogues
+        if (!SPLIT3) {
+          tcgen05_commit_pair(&tfull_bar[acc]);  // accumulators complete -> both epilogues
+          if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (SPLIT3 && warp >= 2 + SPLIT_EPI_WARPS) {
+    // ===== splitters: lo = x - (x truncated to TF32) for every element of the stage, written behind it =====
+    constexpr int NT = SPLIT_SPLIT_WARPS * 32;
+    constexpr int PER = (int)(SPLIT_TILE_BYTES / 16 + NT - 1) / NT;  // 16-byte vectors per thread and stage: 8
+    const int t = (int)threadIdx.x - (2 + SPLIT_EPI_WARPS) * 32;
+    uint32_t stage = 0, phase = 0;
+    ChunkWalk walk(pair, (int)(gridDim.x >> 1), total_cols, n, wmax);
+    int rb, n0, w;
+    while (walk.next(rb, n0, w)) {
+      const int vecs = (int)(A_BYTES2 + (uint32_t)(w >> 1) * BK * 4) >> 4;  // A tile and this CTA's half of B are contiguous
+      for (int kb = 0; kb < num_kb; kb++) {
+        mbar_wait(&full_bar[stage], phase);
+        const float4* src = reinterpret_cast<const float4*>(smem + stage * SB);
+        float4* dst = reinterpret_cast<float4*>(smem + stage * SB + HB);
+        float4 x[PER];
+#pragma unroll
+        for (int u = 0; u < PER; u++)
+          if (t + u * NT < vecs) x[u] = src[t + u * NT];
+#pragma unroll
+        for (int u = 0; u < PER; u++)
+          if (t + u * NT < vecs) {
+            float4 lo;
+            lo.x = tf32_lo(x[u].x), lo.y = tf32_lo(x[u].y), lo.z = tf32_lo(x[u].z), lo.w = tf32_lo(x[u].w);
+            dst[t + u * NT] = lo;
+          }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(&split_bar[stage]), 0));
+        if (++stage == NST) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (SPLIT3) {
+    // ===== epilogue, SPLIT3: the chunks of the contraction summed in registers (round to nearest), then the stores.
+    // Eight warps: warp e works on TMEM lanes [32 (warp % 4), +32) — the only ones it may touch — and columns [64 (e / 4), +64)
+    const int quad = warp & 3, col0 = ((warp - 2) >> 2) * 64;
+    uint32_t acc = 0, acc_phase = 0;
+    ChunkWalk walk(pair, (int)(gridDim.x >> 1), total_cols, n, wmax);
+    int rb, n0, w;
+    const int nchunk = (num_kb + SPLIT_KC - 1) / SPLIT_KC;
+    while (walk.next(rb, n0, w)) {
+      const int m0 = rb * 256 + (int)rank * BM;
+      float sum[64];
+      for (int ch = 0; ch < nchunk; ch++) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t t0 = tmem_base + acc * 256 + col0 + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          if (col0 + c * 16 < w) {
+            uint32_t hi[16], lo[16];
+            tmem_ld_32x32b_x16(t0 + c * 16, hi);
+            tmem_ld_32x32b_x16(t0 + 128 + c * 16, lo);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const float part = __fadd_rn(__uint_as_float(hi[j]), __uint_as_float(lo[j]));
+              sum[c * 16 + j] = ch == 0 ? part : __fadd_rn(sum[c * 16 + j], part);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+          else mbar_arrive_remote(map_to_cta(smem_u32(&tempty_bar[acc]), 0));  // once per chunk: no cluster-scope membar
+        }
         if (++acc == ACC_STAGES) acc = 0, acc_phase ^= 1;
+      }
+      float* crow = C + (size_t)(n0 + col0) * ldc + m0 + quad * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        if (col0 + c * 16 < w) {
+          float* cp = crow + (size_t)(c * 16) * ldc;
+          if (epi_mode == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) cp[(size_t)j * ldc] = sum[c * 16 + j];
+          } else {
+            float old[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) old[j] = cp[(size_t)j * ldc];
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+              cp[(size_t)j * ldc] = epi_mode == 1 ? __fsub_rn(old[j], __fmul_rn(sum[c * 16 + j], lr)) : __fadd_rn(old[j], sum[c * 16 + j]);
+          }
+        }
       }
     }
   } else {
@@ -605,28 +779,29 @@ void launch_bn(const float* A, bool ta, const float* B, bool tb, float* C, int m
   else launch_variant<BN, false, true>(ma, mb, C, m, n, k, ldc, epi, stream);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool SPLIT3>
 void launch_pair_variant(const CUtensorMap& ma, const CUtensorMap& mb_big, const CUtensorMap& mb_small, float* C, int m, int n,
                          int k, int ldc, const GemmEpilogue& epi, int wmax, int pairs, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)STAGES2 * STAGE_BYTES2 + 256 + 1024;
+  constexpr size_t smem = (size_t)(SPLIT3 ? SPLIT_STAGES * 2 * SPLIT_TILE_BYTES : STAGES2 * STAGE_BYTES2) + 256 + 1024;
   static bool configured = false;
   if (!configured) {
-    CG_CUDA(cudaFuncSetAttribute(gemm_tf32_pair_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CG_CUDA(cudaFuncSetAttribute(gemm_tf32_pair_kernel<A_MN, B_MN, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(SPLIT3 ? PAIR_THREADS_SPLIT3 : PAIR_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;  // the CTA pair: two SMs of one TPC
+  attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_pair_kernel<A_MN, B_MN>, ma, mb_big, mb_small, C, m, n, k, ldc, epi.mode, epi.lr, wmax));
+  CG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_pair_kernel<A_MN, B_MN, SPLIT3>, ma, mb_big, mb_small, C, m, n, k, ldc, epi.mode, epi.lr,
+                             wmax));
 }
 
 // On by default (cg_set_tf32_pair(0) selects the single-CTA kernel for every shape). A dense GEMM on this 1 kW part runs
@@ -639,25 +814,27 @@ void launch_pair_variant(const CUtensorMap& ma, const CUtensorMap& mb_big, const
 int g_pair_enabled = 1;
 bool pair_kernel_enabled() { return g_pair_enabled != 0; }
 
-bool pair_eligible(int m, int n, int k) { return pair_kernel_enabled() && m % 256 == 0 && n % 64 == 0 && k % BK == 0; }
+bool pair_shape(int m, int n, int k) { return m % 256 == 0 && n % 64 == 0 && k % BK == 0; }
+bool pair_eligible(int m, int n, int k) { return pair_kernel_enabled() && pair_shape(m, n, k); }
 
+template <bool SPLIT3>
 void launch_pair(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda, int ldb, int ldc,
                  const GemmEpilogue& epi, cudaStream_t stream) {
   const bool a_mn = !ta, b_mn = tb;
   const int total = (m / 256) * n;
   // widest column tile <= 256 that divides n (K-major B halves need 16-row boxes, MN-major 32-column chunks)
   const int gran = b_mn ? 64 : 32;
-  int wmax = 256;
+  int wmax = SPLIT3 ? 128 : 256;  // SPLIT3 keeps hi and lo accumulators of two chunks in the 512 TMEM columns
   while (wmax > gran && n % wmax != 0) wmax -= gran;
   const int tiles = total / wmax;
   const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
   const CUtensorMap ma = make_operand_map(A, a_mn, m, k, lda, BM);
   const CUtensorMap mb_big = make_operand_map(B, b_mn, n, k, ldb, wmax / 2);
   const CUtensorMap mb_small = make_operand_map(B, b_mn, n, k, ldb, b_mn ? 32 : 16);
-  if (a_mn && !b_mn) launch_pair_variant<true, false>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
-  else if (a_mn && b_mn) launch_pair_variant<true, true>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
-  else if (!a_mn && !b_mn) launch_pair_variant<false, false>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
-  else launch_pair_variant<false, true>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
+  if (a_mn && !b_mn) launch_pair_variant<true, false, SPLIT3>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
+  else if (a_mn && b_mn) launch_pair_variant<true, true, SPLIT3>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
+  else if (!a_mn && !b_mn) launch_pair_variant<false, false, SPLIT3>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
+  else launch_pair_variant<false, true, SPLIT3>(ma, mb_big, mb_small, C, m, n, k, ldc, epi, wmax, pairs, stream);
 }
 
 }  // namespace
@@ -679,9 +856,19 @@ void launch_gemm_tf32(const float* A, bool ta, const float* B, bool tb, float* C
                       int ldc, const GemmEpilogue& epi, cudaStream_t stream) {
   if (!gemm_tf32_aligned(A, B, lda, ldb))
     throw Error("tcgen05 product: operands must be 128-byte aligned with leading dimensions in multiples of 4");
-  if (pair_eligible(m, n, k)) return launch_pair(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
+  if (pair_eligible(m, n, k)) return launch_pair<false>(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
   if (n % 256 == 0) launch_bn<256>(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
   else launch_bn<128>(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
+}
+
+// FP32-accurate product on the tensor core (SPLIT3 above): the CTA-pair kernel only.
+bool gemm_tf32x3_eligible(int m, int n, int k, bool ta, bool tb) { return gemm_tf32_eligible(m, n, k, ta, tb) && pair_shape(m, n, k); }
+
+void launch_gemm_tf32x3(const float* A, bool ta, const float* B, bool tb, float* C, int m, int n, int k, int lda, int ldb, int ldc,
+                        const GemmEpilogue& epi, cudaStream_t stream) {
+  if (!gemm_tf32_aligned(A, B, lda, ldb))
+    throw Error("tcgen05 product: operands must be 128-byte aligned with leading dimensions in multiples of 4");
+  launch_pair<true>(A, ta, B, tb, C, m, n, k, lda, ldb, ldc, epi, stream);
 }
 
 }  // namespace cg

@@ -83,7 +83,7 @@ void set_plan_only(bool on);
 struct Runtime {
   cudaStream_t stream = nullptr;
   int mode = 0;          // 0 = exact (the reference's tree walk), 1 = dag (memoised)
-  int tf32 = 0;          // 0 = FP32 SIMT products, 1 = tcgen05 TF32 where eligible
+  int tf32 = 0;          // 0 = FP32 SIMT products, 1 = tcgen05 TF32 where eligible, 2 = FP32-accurate 3 x TF32 on the tensor core
   int fix_act_grad = 0;  // 0 = reproduce Q3
   int fix_broadcast_sum = 0;  // 0 = reproduce Q5 in the backward pass (scalar <- matrix error = mean); 1: sum
   int fix_sub_sign = 0;       // 0 = reproduce Q4's `0 - x -> x`; 1: `0 - x -> -x`

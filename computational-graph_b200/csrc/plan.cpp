@@ -1273,7 +1273,7 @@ void plan_launch_step(Plan& p, size_t index, cudaStream_t stream) {
         epi.lr = s.ins.imm;
         if (s.ins.epi && p.vals[s.ins.c_in].ptr != c.ptr) throw Error("internal: gemm epilogue operand is not in place");
         launch_gemm(a.ptr, s.ins.ta, b.ptr, s.ins.tb, c.ptr, m, n, k, (int)a.sh.h, (int)b.sh.h, (int)c.sh.h, epi,
-                    p.tf32 != 0, stream);
+                    p.tf32, stream);
       } break;
       case Step::ALLREDUCE: dp_allreduce_sum(p.vals[s.ins.dst].ptr, p.vals[s.ins.dst].sh.n(), stream); break;
       case Step::DPUPDATE:

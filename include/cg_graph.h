@@ -93,7 +93,9 @@ int cg_kind(const cg_function *f);
 
 /* ---- execution switches (defaults reproduce the reference; also CG_MODE / CG_TF32 / … env) ------- */
 void cg_set_mode(int mode);           /* 0 = exact (the reference's tree walk), 1 = dag (memoised, visit-once) */
-void cg_set_tf32(int on);             /* 1: tcgen05 TF32 tensor-core products for eligible shapes */
+void cg_set_tf32(int on);             /* 1: tcgen05 TF32 tensor-core products for eligible shapes; 2: FP32-accurate products on the
+                                       * tensor core for eligible shapes (every operand split into the part TF32 keeps and the
+                                       * part it drops, three MMAs per k-step: ~1e-6 per term, 1/3 of the TF32 rate) */
 void cg_set_fix_act_grad(int on);     /* 1: sigmoid/tanh pass error*derivative (repairs Q3) */
 /* Corrected-semantics switches, each off by default so that the reference is reproduced:
  * broadcast_sum: in the backward pass a scalar that absorbs a matrix-shaped error takes its SUM (the gradient of a

@@ -174,3 +174,47 @@ def test_gemm_tcgen05_tf32(cg, abis, dims, t1, t2, pair):
     finally:
         cg.set_tf32(False)
         cg.set_tf32_pair(True)
+
+
+@pytest.mark.parametrize("t1,t2", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("dims", [(256, 256, 128), (1024, 768, 512), (512, 832, 96 + 32), (1024, 1408, 160), (2048, 4096, 128),
+                                  (256, 4096, 4096)])
+def test_gemm_tcgen05_tf32x3(cg, abis, dims, t1, t2):
+    """FP32-accurate product on the tensor core (cg_set_tf32(2): every operand split in shared memory into the part TF32
+    keeps and the part it drops, three tcgen05.mma per k-step, the contraction accumulated in 256-deep chunks that are
+    summed round-to-nearest in registers; CTA-pair kernel). Small-integer inputs must be EXACT (any layout / barrier
+    error of the split tiles shows); operands that NEED the dropped bits (1 + 2^-12 against 1: plain TF32 returns k)
+    must be exact too; uniform inputs are held, element by element, to 1.5e-6 of sum |a||b| (the term left out,
+    lo_a lo_b, is < 2^-20 |a||b| and 2^-22 on average; the first version, one accumulator for the whole contraction,
+    failed this at k = 4096 by 2.4x through the tensor core's truncating accumulation) and to 1e-5 in the max norm."""
+    p, _ = abis
+    cg.set_tf32(2)
+    try:
+        m, n, k = dims
+        rng = np.random.default_rng(m + 3 * n + 7 * k)
+        for case in ("int", "lowbits", "uniform"):
+            if case == "int":
+                a = rng.integers(-4, 5, (k, m) if t1 else (m, k)).astype(np.float32)
+                b = rng.integers(-4, 5, (n, k) if t2 else (k, n)).astype(np.float32)
+            elif case == "lowbits":
+                a = (1.0 + rng.integers(0, 2, (k, m) if t1 else (m, k)) * 2.0 ** -12).astype(np.float32)
+                b = rng.integers(-1, 2, (n, k) if t2 else (k, n)).astype(np.float32)
+            else:
+                a = rng.uniform(-1, 1, (k, m) if t1 else (m, k)).astype(np.float32)
+                b = rng.uniform(-1, 1, (n, k) if t2 else (k, n)).astype(np.float32)
+            ap, bp, rp = p.new(*a.shape, a), p.new(*b.shape, b), p.new(m, n)
+            p.lib.fill_matrix(C.byref(rp), np.float32(np.nan))
+            p.lib.gemm(C.byref(ap), t1, C.byref(bp), t2, C.byref(rp))
+            a64, b64 = (a.T if t1 else a).astype(np.float64), (b.T if t2 else b).astype(np.float64)
+            want = a64 @ b64
+            got = p.get(rp).astype(np.float64)
+            if case != "uniform":
+                assert np.array_equal(got, want), (case, dims, t1, t2, float(np.max(np.abs(got - want))))
+            else:
+                bound = 1.5e-6 * (np.abs(a64) @ np.abs(b64))
+                assert np.all(np.abs(got - want) <= bound), (dims, t1, t2, float(np.max(np.abs(got - want) / bound)))
+                assert rel_err(got, want) < 1e-5
+            for x in (ap, bp, rp):
+                p.free(x)
+    finally:
+        cg.set_tf32(False)

@@ -81,13 +81,16 @@ def _t8_oracle(oracle):
     return _T8
 
 
-@pytest.mark.parametrize("product,tol", [("f32", 1e-5), ("tf32", 1e-3)])
+PRODUCT = {"f32": 0, "tf32": 1, "tf32x3": 2}  # cg_set_tf32: FP32 SIMT | TF32 | FP32-accurate 3 x TF32 on the tensor core
+
+
+@pytest.mark.parametrize("product,tol", [("f32", 1e-5), ("tf32", 1e-3), ("tf32x3", 1e-5)])
 def test_lstm_T8_error_growth_against_the_oracle(cg, oracle, product, tol):
     """LSTM T = 8, B = 256, H = I = 512, dag mode: eight chained time steps of tensor-core products against the f32 CPU
     oracle — loss trajectory of two iterations, the first iteration's per-leaf gradients and the leaves after the second."""
     want = _t8_oracle(oracle)
     cg.set_mode("dag")
-    cg.set_tf32(product == "tf32")
+    cg.set_tf32(PRODUCT[product])
     fg = readme_lstm(cg, 512, T=8, seed=808, batch=256, d_in=512, scale=1.0 / np.sqrt(512))
     st = cg.plan_stats(fg, LR)
     assert st["gemms"] > 0 and st["vm_resident"] == 0
@@ -106,7 +109,7 @@ def test_lstm_T8_error_growth_against_the_oracle(cg, oracle, product, tol):
         assert close_err(after2[k], want["after2"][k], tol) <= slack, k
 
 
-@pytest.mark.parametrize("product,tol", [("tf32", 1e-3), ("f32", 1e-5)])
+@pytest.mark.parametrize("product,tol", [("tf32", 1e-3), ("f32", 1e-5), ("tf32x3", 1e-5)])
 def test_c4_full_size_iteration_against_float64(cg, product, tol):
     """BASELINE config 4 at FULL size (H = I = 4096, T = 8, B = 1024, dag mode, 1/sqrt(H)-scaled weights): the forward value
     and every leaf's gradient of one iteration against the float64 restatement (tests/f64_graph.py, pinned to
@@ -119,7 +122,7 @@ def test_c4_full_size_iteration_against_float64(cg, product, tol):
     before = [np.array(v, dtype=np.float32) for _, v in fd.leaves()]
     td = np.asarray(fd.minimize({}, LR, 1, trace=True))
     cg.set_mode("dag")
-    cg.set_tf32(product == "tf32")
+    cg.set_tf32(PRODUCT[product])
     fg = readme_lstm(cg, Hd, T=T, seed=4, batch=B, d_in=Hd, scale=scale)
     tg = np.asarray(fg.minimize({}, LR, 1, trace=True))
     slack = TF32_PER_ELEMENT_SLACK if product == "tf32" else 1.0

@@ -1,7 +1,7 @@
 """Times the three products of the hot path (forward X.W, dX = E.W^T, dW = X^T.E; optimize.rs:135,197-198) through the
 26-symbol ABI's `gemm` at the BASELINE config-4 shapes. Also the small command `ncu --set full` is pointed at.
 
-    python tools/gemm_bench.py [--reps 50] [--product tf32|f32] [--b 1024] [--h 4096]
+    python tools/gemm_bench.py [--reps 50] [--product tf32|tf32x3|f32] [--b 1024] [--h 4096]
 """
 import argparse
 import ctypes as C
@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--h", type=int, default=4096)
     args = ap.parse_args()
     api = pkg.get_api()
-    api.set_tf32(args.product == "tf32")
+    api.set_tf32({"f32": 0, "tf32": 1, "tf32x3": 2}[args.product])
     p = ProductMatrixAbi(api.lib)
     B, H = args.b, args.h
     rng = np.random.default_rng(0)

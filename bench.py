@@ -262,9 +262,12 @@ def measure_lstm(api, torch, dist, wl: Workload, product: str, steps: int, warmu
     cfg = wl.config()
     cfg["product"] = product
     cfg["parallelism"] = f"dp{world}" if world > 1 else "single"
-    traffic = None
-    if product == "tf32" and wl.rows == 1024:
-        traffic = 88.86e6   # profiles/r01_gemm_tf32_full.raw.txt: 83.9 MB read + 5.0 MB written per launch
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant product, from the committed `ncu --set full`
+    # captures (per launch, like `achieved`)
+    traffic = {("tf32", 1024): 88.86e6,      # profiles/r01_gemm_tf32_full.raw.txt: 83.9 MB read + 5.0 MB written
+               ("tf32", 8192): 737.3e6,      # profiles/r02d_gemm_pair_full.raw.txt: 617 MB + 120 MB (335 MB algorithmic: B re-read per row-block wave)
+               ("tf32x3", 8192): 1027.6e6,   # profiles/r02l_gemm_tf32x3_full.raw.txt: 900 MB + 128 MB
+               }.get((product, wl.rows))
     line = {
         "metric": METRIC, "value": agg * 1000.0 / ms, "unit": "iterations/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,

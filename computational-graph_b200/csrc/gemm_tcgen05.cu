@@ -365,8 +365,8 @@ __device__ __forceinline__ float tf32_lo(float x) {
 // The tile sequence of one pair (static round-robin over (row-block, column-tile)): every role of both CTAs walks
 // the same list. Consecutive pairs take consecutive column tiles of one row-block, so they share its A rows in L2.
 // (Tried and dropped, profiles/r02m_tile_order_prefetch.txt: taking the row-blocks in bands so that B streams past an
-// L2-resident A panel, and L2 prefetch of later k-blocks — DRAM reads fall, the rate does not move: the kernels run
-// against the power cap, not against operand latency.)
+// L2-resident A panel, and L2 prefetch of later k-blocks — the rate does not move (prefetch costs 3-6 %): the kernels
+// run against the power cap, not against operand latency.)
 struct ChunkWalk {
   int t, ntiles, stride, tiles_n, wmax;
   __device__ __forceinline__ ChunkWalk(int pair, int npairs, int total_cols, int n, int wmax_) : wmax(wmax_) {

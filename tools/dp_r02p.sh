@@ -1,10 +1,10 @@
-# round 2, N GPUs: two alternating exchange lanes + pair kernel + 32 work queues — the driver's command line, with parity
+# round 2, N GPUs: the driver's command line at head (pair kernel, 32 work queues, in-run parity, exchange vs ncclAllReduce)
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 900 $TR --master-port 29801 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02k_bench_c5_n$N.json 2> gpurun_out/r02k_bench_c5_n$N.err; echo "bench rc=$?"
-tail -3 gpurun_out/r02k_bench_c5_n$N.err | cut -c1-300
-python - gpurun_out/r02k_bench_c5_n$N.json <<'PY'
+timeout 900 $TR --master-port 29801 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02p_bench_c5_n$N.json 2> gpurun_out/r02p_bench_c5_n$N.err; echo "bench rc=$?"
+tail -3 gpurun_out/r02p_bench_c5_n$N.err | cut -c1-300
+python - gpurun_out/r02p_bench_c5_n$N.json <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
@@ -14,4 +14,9 @@ try:
     print("  clocks", d["clocks"])
 except Exception as e:
     print("  unreadable:", e)
+PY
+python - gpurun_out/r02p_bench_c5_n$N.json <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print("  exchange_vs_nccl", d.get("exchange_vs_nccl"))
 PY

@@ -109,18 +109,30 @@ def test_lstm_T8_error_growth_against_the_oracle(cg, oracle, product, tol):
         assert close_err(after2[k], want["after2"][k], tol) <= slack, k
 
 
+_C4_F64 = {}
+
+
+def _c4_float64(B, Hd, T, scale):
+    """One iteration of config 4 on the float64 restatement (6 TFLOP of float64 BLAS: computed once for the three product
+    variants): leaf names, leaves before, the trace, leaves after."""
+    if not _C4_F64:
+        from f64_graph import get_f64
+        fd = readme_lstm(get_f64(), Hd, T=T, seed=4, batch=B, d_in=Hd, scale=scale)
+        names = [n for n, _ in fd.leaves()]
+        before = [np.array(v, dtype=np.float32) for _, v in fd.leaves()]
+        td = np.asarray(fd.minimize({}, LR, 1, trace=True))
+        _C4_F64.update(names=names, before=before, td=td, fd=fd)  # fd keeps the float64 leaves: no second copy of 9 GB
+    return _C4_F64["names"], _C4_F64["before"], _C4_F64["td"], [v for _, v in _C4_F64["fd"].leaves()]
+
+
 @pytest.mark.parametrize("product,tol", [("tf32", 1e-3), ("f32", 1e-5), ("tf32x3", 1e-5)])
 def test_c4_full_size_iteration_against_float64(cg, product, tol):
     """BASELINE config 4 at FULL size (H = I = 4096, T = 8, B = 1024, dag mode, 1/sqrt(H)-scaled weights): the forward value
     and every leaf's gradient of one iteration against the float64 restatement (tests/f64_graph.py, pinned to
     cg_oracle.c in the CPU tier) — the C oracle itself would need an hour on one core for this iteration."""
-    from f64_graph import get_f64
     B, Hd, T = 1024, 4096, 8
     scale = 1.0 / np.sqrt(Hd)
-    fd = readme_lstm(get_f64(), Hd, T=T, seed=4, batch=B, d_in=Hd, scale=scale)
-    names = [n for n, _ in fd.leaves()]
-    before = [np.array(v, dtype=np.float32) for _, v in fd.leaves()]
-    td = np.asarray(fd.minimize({}, LR, 1, trace=True))
+    names, before, td, after = _c4_float64(B, Hd, T, scale)
     cg.set_mode("dag")
     cg.set_tf32(PRODUCT[product])
     fg = readme_lstm(cg, Hd, T=T, seed=4, batch=B, d_in=Hd, scale=scale)
@@ -131,7 +143,7 @@ def test_c4_full_size_iteration_against_float64(cg, product, tol):
     got = fg.leaves()
     assert [n for n, _ in got] == names
     worst = ("", 0.0)
-    for (n, vg), b, (_, vd) in zip(got, before, fd.leaves()):
+    for (n, vg), b, vd in zip(got, before, after):
         e = update_err(b, vg, vd, tol)
         if e > worst[1]:
             worst = (n, e)
